@@ -1,0 +1,153 @@
+"""CPU tests: the oracle against the reference's known-answer vectors and against SciPy."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle import oracle
+from arrow_matrix_b200 import synth, graphio
+
+
+# ---- routing-table KATs asserted by the reference's tests/test_arrowmpi.py:24-47 -----------------
+def test_all_to_all_tables_reversed_kat():
+    ranks, prev_ranks, rpr, cols = 2, 6, 4, 6
+    perm = np.asarray(list(reversed(range(ranks * rpr))))
+    for i in range(ranks):
+        sl = perm[i * rpr:(i + 1) * rpr]
+        counts, displs, p, out_p = oracle.all_to_all_tables(sl, rpr, cols, prev_ranks + ranks, prev_ranks)
+        assert counts[ranks + prev_ranks - i - 1] == rpr * cols
+        assert sum(counts) == rpr * cols
+        assert displs[ranks + prev_ranks - i - 1] == 0
+        counts, displs, p, out_p = oracle.all_to_all_tables(sl, rpr, cols, ranks + prev_ranks, 0)
+        assert counts[ranks - i - 1] == rpr * cols
+        assert sum(counts) == rpr * cols
+        assert displs[ranks - i - 1] == 0
+
+
+def test_all_to_all_tables_exact_values():
+    # values listed in SURVEY.md 8c (computed from the reference source)
+    c, d, sp, rp = oracle.all_to_all_tables(np.array([7, 6, 5, 4]), 4, 6, 8, 6)
+    assert c == [0, 0, 0, 0, 0, 0, 0, 24] and d == [0] * 8
+    assert list(sp) == [0, 1, 2, 3] and list(rp) == [3, 2, 1, 0]
+    c, d, sp, rp = oracle.all_to_all_tables(np.array([7, 6, 5, 4]), 4, 6, 8, 0)
+    assert c == [0, 24, 0, 0, 0, 0, 0, 0] and d == [0, 0, 24, 24, 24, 24, 24, 24]
+    c, d, sp, rp = oracle.all_to_all_tables(np.array([3, 2, 1, 0]), 4, 6, 8, 6)
+    assert c == [0, 0, 0, 0, 0, 0, 24, 0] and d == [0, 0, 0, 0, 0, 0, 0, 24]
+    # sentinel handling
+    c, d, sp, rp = oracle.all_to_all_tables(np.array([5, 999, 0, 6, 999, 1, 4, 2]), 8, 3, 3, 0)
+    assert c == [18, 0, 0] and d == [0, 18, 18]
+    assert list(sp) == [0, 2, 3, 5, 6, 7, 1, 4] and list(rp) == [2, 5, 7, 6, 0, 3]
+
+
+def test_all_to_all_tables_random_like_reference_test():
+    # the randomised half of tests/test_arrowmpi.py:50-94
+    rng = np.random.default_rng(0)
+    ranks, prev_ranks, rpr, cols = 2, 6, 4, 6
+    perm = 2 * np.arange(ranks * rpr)
+    rng.shuffle(perm)
+    for i in range(ranks):
+        sl = perm[i * rpr:(i + 1) * rpr]
+        counts, displs, p, out_p = oracle.all_to_all_tables(sl, rpr, cols, ranks + prev_ranks, 0)
+        after = sl[p] // rpr
+        assert list(after) == sorted(sl // rpr)
+        for j in range(ranks):
+            assert counts[j] == np.count_nonzero(after == j) * cols
+
+
+# ---- arithmetic: the C restatement against SciPy itself ------------------------------------------
+@pytest.mark.parametrize("k", [1, 4, 10, 16, 128])
+def test_c_kernel_matches_scipy_bitwise(k):
+    rng = np.random.default_rng(42)
+    A = synth.generate_sparse_matrix(500, 500, 5000, np.float32, rng)
+    X = synth.generate_dense_matrix(500, k, np.float32, rng)
+    got = oracle.csr_spmm_c(A, X)
+    ref = A @ X
+    assert got.dtype == np.float32
+    assert np.array_equal(got, ref), np.abs(got - ref).max()
+
+
+def test_c_kernel_int64_indices_and_empty_rows():
+    rng = np.random.default_rng(1)
+    A = sparse.random(64, 64, density=0.05, format="csr", dtype=np.float32, random_state=3)
+    A.indices = A.indices.astype(np.int64)
+    A.indptr = A.indptr.astype(np.int64)
+    X = rng.random((64, 8), dtype=np.float32)
+    assert np.array_equal(oracle.csr_spmm_c(A, X), A @ X)
+    Z = sparse.csr_matrix((5, 5), dtype=np.float32)
+    assert np.array_equal(oracle.csr_spmm_c(Z, np.ones((5, 3), np.float32)), np.zeros((5, 3), np.float32))
+
+
+# ---- loader semantics -------------------------------------------------------------------------------
+def test_number_of_blocks_and_masks():
+    dec = synth.synth_decomposition(6, 8, levels=2, perm_kind="random", seed=1)
+    assert oracle.number_of_blocks(dec[0][0], 8) == 6
+    assert oracle.number_of_blocks(dec[1][0], 8) == 3
+    M = oracle.arrow_mask(dec[0][0], 8, 6)
+    assert M.nnz == dec[0][0].nnz       # the generator is exactly arrow shaped
+
+
+def test_prepare_permutations_one_based_and_padding():
+    p0 = np.arange(1, 11)          # one based, shorter than 2*8 rows
+    p1 = np.array([3, 1, 2, 5, 4, 7, 6, 9, 8, 10])
+    perms, to_prev, to_next, sent = oracle.prepare_permutations([p0, p1], [2, 1], 8)
+    assert perms[0].tolist() == list(range(16))
+    assert perms[1][:10].tolist() == [2, 0, 1, 4, 3, 6, 5, 8, 7, 9] and perms[1][10:].tolist() == list(range(10, 16))
+    assert sent == 32
+    assert to_prev[1].tolist() == perms[1].tolist()       # level 0 is the identity
+    # to_next of level 0: rows of level 1 beyond n_blocks[1]*w = 8 are the sentinel
+    inv1 = np.argsort(perms[1])
+    exp = np.where(inv1 >= 8, 32, inv1)
+    assert to_next[0].tolist() == exp.tolist()
+
+
+# ---- protocol oracle vs the reference tests' own golden (compute_spmm) ------------------------------
+@pytest.mark.parametrize("perm_kind", ["identity", "random", "local"])
+@pytest.mark.parametrize("blockwise", [False, True])
+def test_protocol_matches_compute_spmm(perm_kind, blockwise):
+    w, t0, k = 8, 6, 4
+    dec = synth.synth_decomposition(t0, w, levels=3, perm_kind=perm_kind, seed=11)
+    n = t0 * w
+    rng = np.random.default_rng(42)
+    X = np.round(rng.random((n, k), dtype=np.float32), 0)    # integer valued -> exact (test_arrowmpi.py:259-260)
+    po = oracle.ReferenceProtocolOracle(dec, w, k, blockwise=blockwise)
+    assert po.dropped_nnz == [0, 0, 0]
+    Xcur = X
+    for _ in range(3):                                       # chained like test_arrowmpi.py:164-166
+        po.set_features(Xcur[po.perms[0]])
+        C0 = po.step()
+        gold = oracle.compute_spmm(dec, Xcur)
+        got = oracle.to_original_order(C0, po.perms[0], n)
+        assert np.allclose(got, gold)
+        Xcur = gold
+
+
+def test_protocol_level_tiles_after_propagate():
+    # after step() + _propagate_features(), level j holds golden_C[perm_j] (test_arrowmpi.py:306-309)
+    w, t0, k = 8, 4, 3
+    dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=5, shrink=1)
+    n = t0 * w
+    X = np.random.default_rng(3).random((n, k), dtype=np.float32)
+    po = oracle.ReferenceProtocolOracle(dec, w, k)
+    po.set_features(X[po.perms[0]])
+    po.step()
+    po.propagate_features()
+    gold = oracle.compute_spmm(dec, X)
+    assert np.allclose(po.C[1], gold[po.perms[1]][: po.rows[1]], rtol=1e-5, atol=1e-6)
+
+
+def test_npy_layout_roundtrip(tmp_path):
+    dec = synth.synth_decomposition(4, 8, levels=2, perm_kind="random", seed=2)
+    base = str(tmp_path / "synth")
+    graphio.save_decomposition_new(dec, base, 8, block_diagonal=True)
+    assert (tmp_path / "synth_B_8_0_bd_indptr.npy").exists()
+    back = graphio.load_decomposition_new(base, 8, True)
+    assert len(back) == 2
+    for (B, p), (B2, p2) in zip(dec, back):
+        assert np.array_equal(B.indptr, B2.indptr) and np.array_equal(B.indices, B2.indices) and np.array_equal(B.data, B2.data) and np.array_equal(p, p2)
+    mm = graphio.load_decomposition_new(base, 8, True, mem_map=True)
+    assert np.array_equal(np.asarray(mm[1][0][1]), dec[1][0].indices)
+    # Julia converter quirks: no data file, int64 indices, 1-based permutation
+    base2 = str(tmp_path / "jl")
+    graphio.save_decomposition_new(dec, base2, 8, True, write_data=False, index_dtype=np.int64, one_based_permutation=True)
+    back2 = graphio.load_decomposition_new(base2, 8, True)
+    assert back2[0][0].indices.dtype == np.int64 and np.all(back2[0][0].data == 1.0)
+    assert back2[0][1].min() == 1
