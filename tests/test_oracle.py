@@ -149,5 +149,7 @@ def test_npy_layout_roundtrip(tmp_path):
     base2 = str(tmp_path / "jl")
     graphio.save_decomposition_new(dec, base2, 8, True, write_data=False, index_dtype=np.int64, one_based_permutation=True)
     back2 = graphio.load_decomposition_new(base2, 8, True)
-    assert back2[0][0].indices.dtype == np.int64 and np.all(back2[0][0].data == 1.0)
+    assert np.all(back2[0][0].data == 1.0) and back2[0][0].data.dtype == np.float32
+    raw = graphio.load_decomposition_new(base2, 8, True, mem_map=True)
+    assert raw[0][0][0] is None and raw[0][0][1].dtype == np.int64 and raw[0][0][2].dtype == np.int64
     assert back2[0][1].min() == 1
