@@ -1,0 +1,1546 @@
+// libarrow_b200.so -- hand-written sm_100a kernels + C ABI for the arrow-decomposed SpMM hot path.
+//
+// What each piece replaces in the reference (spcl/arrow-matrix, paths relative to /root/reference):
+//   k_spmm_*            scipy `csr @ dense` / cupy->cuSPARSE SpMM at arrow_slim_mpi.py:109-111,125-127,
+//                       142-144,190,211,231 and arrow_mpi.py:198-219,250-269,289-291,323
+//   csr upload (once)   common/sp2cp.py:6-16 (_sp2cp, redone every iteration by the reference)
+//   rowmap epilogue     arrow_dec_mpi.py:421,437  (pack + alltoallv + `C_i[perm] += recvbuf`)
+//   remapped columns    arrow_dec_mpi.py:526,544  (`feature_tile()[perm]` + `C_i[perm] = recvbuf`)
+//   k_gather_rows*      the same two exchanges as standalone (un-fused / cross-GPU) steps
+//
+// Layout: CSR = int32 indptr (rebased to 0) / int32 indices / fp32 values; dense tiles row-major fp32.
+// All kernels are HBM/L2-bandwidth bound gathers (about 2 FLOP/B): no tensor cores on purpose.
+#include "../../include/arrow_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// context + handle tables
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct DenseBuf {
+    float *p = nullptr;
+    int64_t rows = 0;
+    int k = 0;
+    bool owned = false;
+    bool ipc = false;
+    bool live = false;
+};
+
+struct LongTask {      // one segment of a long row
+    int row;
+    int begin;         // nnz offsets (rebased)
+    int end;
+    int slot;          // partial-sum slot
+};
+
+struct Csr {
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    int *indptr = nullptr;
+    int *indices = nullptr;
+    float *vals = nullptr;
+    bool owns_indptr = false, owns_indices = false, owns_vals = false;
+    bool may_skip = false;            // indices may contain -1 (remapped through a partial map)
+    int64_t max_row_nnz = 0;
+    // long rows (nnz > threshold) are processed by whole CTAs in segments, then reduced in order
+    int n_long_rows = 0;
+    int n_long_tasks = 0;
+    LongTask *long_tasks = nullptr;   // device
+    int *long_rows = nullptr;         // device: row ids
+    int *long_first = nullptr;        // device: first slot of each long row (n_long_rows+1)
+    bool owns_long = false;
+    int long_threshold = 0;
+    bool live = false;
+};
+
+struct IdxMap {
+    int *p = nullptr;
+    int64_t n = 0;
+    int64_t limit = 0;
+    bool live = false;
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct arrow_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    std::string err;
+    std::vector<DenseBuf> dense;
+    std::vector<Csr> csrs;
+    std::vector<IdxMap> maps;
+    Timer timers[ARROW_MAX_TIMERS];
+    int64_t launches = 0;
+    int long_threshold = 1024;
+    int long_segment = 2048;
+    float *long_scratch = nullptr;    // [slots][k] partial sums of long-row segments
+    size_t long_scratch_bytes = 0;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    unsigned int barrier_epoch = 0;
+    int *dev_status = nullptr;        // device-side status word (barrier timeout)
+};
+
+namespace {
+
+int fail(arrow_ctx *ctx, int code, const char *fmt, ...) __attribute__((format(printf, 3, 4)));
+int fail(arrow_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail((ctx), ARROW_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                          \
+    } while (0)
+
+#define CHECK_CTX(ctx)                                                                        \
+    do {                                                                                      \
+        if (!(ctx)) return fail(nullptr, ARROW_ERR_ARG, "null context");                      \
+        cudaError_t _e = cudaSetDevice((ctx)->device);                                        \
+        if (_e != cudaSuccess)                                                                \
+            return fail((ctx), ARROW_ERR_CUDA, "cudaSetDevice(%d): %s", (ctx)->device,        \
+                        cudaGetErrorString(_e));                                              \
+    } while (0)
+
+template <class T>
+int new_slot(std::vector<T> &v) {
+    for (size_t i = 0; i < v.size(); ++i)
+        if (!v[i].live) return (int)i;
+    v.emplace_back();
+    return (int)v.size() - 1;
+}
+
+DenseBuf *get_dense(arrow_ctx *ctx, int h) {
+    if (h < 0 || h >= (int)ctx->dense.size() || !ctx->dense[h].live) return nullptr;
+    return &ctx->dense[h];
+}
+Csr *get_csr(arrow_ctx *ctx, int h) {
+    if (h < 0 || h >= (int)ctx->csrs.size() || !ctx->csrs[h].live) return nullptr;
+    return &ctx->csrs[h];
+}
+IdxMap *get_map(arrow_ctx *ctx, int h) {
+    if (h < 0 || h >= (int)ctx->maps.size() || !ctx->maps[h].live) return nullptr;
+    return &ctx->maps[h];
+}
+
+inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4 &acc, float a, const float4 &x) {
+    acc.x = fmaf(a, x.x, acc.x);
+    acc.y = fmaf(a, x.y, acc.y);
+    acc.z = fmaf(a, x.z, acc.z);
+    acc.w = fmaf(a, x.w, acc.w);
+}
+__device__ __forceinline__ void f4_add(float4 &acc, const float4 &x) {
+    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+}
+
+struct SpmmArgs {
+    const int *__restrict__ indptr;
+    const int *__restrict__ indices;
+    const float *__restrict__ vals;
+    const float *__restrict__ X;
+    float *__restrict__ C;
+    const int *__restrict__ rowmap;   // nullptr: identity
+    long long n_rows;
+    int k;                            // feature columns
+    int k4;                           // k / 4 (vector kernels)
+    int long_threshold;               // rows with more entries are left to the long-row kernels
+};
+
+// ------------------------------------------------------------------------------------------------
+// variant 0: a group of G lanes owns one row; every lane of the group reads the same index/value
+// (hardware broadcast) and its own float4 slice of the X row.  UNROLL independent X gathers in flight.
+// ------------------------------------------------------------------------------------------------
+template <int G, int VPL, bool ROWMAP, bool ACC>
+__global__ void __launch_bounds__(256) k_spmm_direct(SpmmArgs a) {
+    constexpr int RPW = 32 / G;
+    constexpr int UNROLL = (VPL == 1) ? 4 : 2;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;                      // lane inside the group
+    const int gi = lane / G;                      // group inside the warp
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const float4 *__restrict__ X4 = reinterpret_cast<const float4 *>(a.X);
+    float4 *__restrict__ C4 = reinterpret_cast<float4 *>(a.C);
+    const int k4 = a.k4;
+
+    for (long long row = warp_id * RPW + gi; row < a.n_rows; row += warps_total * RPW) {
+        const int s = __ldg(a.indptr + row);
+        const int e = __ldg(a.indptr + row + 1);
+        if (e - s > a.long_threshold) continue;
+        long long orow = row;
+        if (ROWMAP) {
+            orow = __ldg(a.rowmap + row);
+            if (orow < 0) continue;
+        }
+        float4 acc[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) acc[i] = f4_zero();
+
+        for (int p = s; p < e; p += UNROLL) {
+            int c[UNROLL];
+            float v[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const bool ok = p + u < e;
+                c[u] = ok ? __ldcs(a.indices + p + u) : -1;
+                v[u] = ok ? __ldcs(a.vals + p + u) : 0.f;
+            }
+            float4 x[UNROLL][VPL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const int vec = gl + i * G;
+                    x[u][i] = (c[u] >= 0 && vec < k4) ? __ldg(X4 + (long long)c[u] * k4 + vec) : f4_zero();
+                }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int vec = gl + i * G;
+            if (vec < k4) {
+                float4 *dst = C4 + orow * k4 + vec;
+                if (ACC) {
+                    float4 old = *dst;
+                    f4_add(acc[i], old);
+                    *dst = acc[i];
+                } else {
+                    __stcs(dst, acc[i]);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// variant 1: the group loads G consecutive (index, value) pairs of its row with ONE coalesced request
+// each and broadcasts them with width-G shuffles; the X gathers are issued UNROLL at a time.
+// ------------------------------------------------------------------------------------------------
+template <int G, int VPL, bool ROWMAP, bool ACC>
+__global__ void __launch_bounds__(256) k_spmm_shfl(SpmmArgs a) {
+    constexpr int RPW = 32 / G;
+    constexpr int UNROLL = (G >= 4) ? ((VPL == 1) ? 4 : 2) : G;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int gi = lane / G;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const float4 *__restrict__ X4 = reinterpret_cast<const float4 *>(a.X);
+    float4 *__restrict__ C4 = reinterpret_cast<float4 *>(a.C);
+    const int k4 = a.k4;
+
+    // warp-uniform trip count: every lane of the warp runs the same number of row iterations
+    for (long long row0 = warp_id * RPW; row0 < a.n_rows; row0 += warps_total * RPW) {
+        const long long row = row0 + gi;
+        int s = 0, e = 0;
+        long long orow = -1;
+        if (row < a.n_rows) {
+            s = __ldg(a.indptr + row);
+            e = __ldg(a.indptr + row + 1);
+            orow = row;
+            if (ROWMAP) orow = __ldg(a.rowmap + row);
+            if (e - s > a.long_threshold || orow < 0) { e = s; orow = -1; }
+        }
+        const int len = e - s;
+        const int maxlen = __reduce_max_sync(0xffffffffu, len);
+        float4 acc[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) acc[i] = f4_zero();
+
+        for (int base = 0; base < maxlen; base += G) {
+            int myc = -1;
+            float myv = 0.f;
+            if (base + gl < len) {
+                myc = __ldcs(a.indices + s + base + gl);
+                myv = __ldcs(a.vals + s + base + gl);
+            }
+            const int cnt = min(G, maxlen - base);               // warp-uniform
+            for (int u0 = 0; u0 < cnt; u0 += UNROLL) {
+                int c[UNROLL];
+                float v[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    c[u] = __shfl_sync(0xffffffffu, myc, (u0 + u) % G, G);
+                    v[u] = __shfl_sync(0xffffffffu, myv, (u0 + u) % G, G);
+                    if (u0 + u >= G) c[u] = -1;
+                }
+                float4 x[UNROLL][VPL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) {
+                        const int vec = gl + i * G;
+                        x[u][i] = (c[u] >= 0 && vec < k4) ? __ldg(X4 + (long long)c[u] * k4 + vec) : f4_zero();
+                    }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
+            }
+        }
+        if (orow >= 0) {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int vec = gl + i * G;
+                if (vec < k4) {
+                    float4 *dst = C4 + orow * k4 + vec;
+                    if (ACC) {
+                        float4 old = *dst;
+                        f4_add(acc[i], old);
+                        *dst = acc[i];
+                    } else {
+                        __stcs(dst, acc[i]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// variant 2: TMA-style staging.  Each warp stages the X rows its rows reference into shared memory
+// with one cp.async.bulk (UBLKCP) per non-zero, completion tracked by a per-warp mbarrier, two stages
+// deep, and accumulates out of shared memory.  No registers are spent on in-flight gathers.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+constexpr int TMA_WARPS = 8;      // warps per CTA
+constexpr int TMA_SLOTS = 16;     // X rows staged per stage per warp
+constexpr int TMA_STAGES = 2;
+
+// One warp per row (VPL float4 per lane).  The warp walks a stream of work items -- (row, chunk of up
+// to TMA_SLOTS non-zeros) -- and keeps the NEXT item's X rows in flight while it accumulates the
+// current one out of shared memory, so the pipeline spans row boundaries.
+struct TmaItem {
+    long long row;     // -1: end of stream
+    long long orow;
+    int p0;            // first nnz of this chunk
+    int cnt;           // nnz in this chunk
+    int last;          // chunk closes its row
+    int myc;           // this lane's column (lane < cnt), -1 otherwise
+    float myv;
+};
+
+template <int VPL, bool ROWMAP, bool ACC>
+__global__ void __launch_bounds__(TMA_WARPS * 32) k_spmm_tma(SpmmArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int k4 = a.k4;
+    const uint32_t row_bytes = (uint32_t)a.k * 4u;
+    float *wbase = reinterpret_cast<float *>(smem_raw) + (size_t)warp * TMA_STAGES * TMA_SLOTS * a.k;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)TMA_WARPS * TMA_STAGES * TMA_SLOTS * row_bytes) +
+                     warp * TMA_STAGES;
+    if (lane == 0) {
+        for (int st = 0; st < TMA_STAGES; ++st) mbar_init(&bars[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t parity0 = 0u, parity1 = 0u;
+
+    const long long warps_total = (long long)gridDim.x * TMA_WARPS;
+    const long long warp_id = (long long)blockIdx.x * TMA_WARPS + warp;
+    float4 *__restrict__ C4 = reinterpret_cast<float4 *>(a.C);
+
+    // work-item iterator (all lanes hold identical copies)
+    long long it_row = warp_id - warps_total;
+    int it_p = 0, it_e = 0;
+    long long it_orow = -1;
+    auto next_item = [&](TmaItem &t) {
+        while (it_p >= it_e) {                       // advance to the next non-empty, non-long, routed row
+            it_row += warps_total;
+            if (it_row >= a.n_rows) { t.row = -1; t.cnt = 0; t.myc = -1; t.myv = 0.f; t.last = 0; return; }
+            const int s = __ldg(a.indptr + it_row);
+            const int e = __ldg(a.indptr + it_row + 1);
+            long long orow = it_row;
+            if (ROWMAP) orow = __ldg(a.rowmap + it_row);
+            if (orow < 0 || e - s > a.long_threshold) continue;
+            it_orow = orow;
+            it_p = s;
+            it_e = e;
+            if (s == e) {                            // empty row still has to store zeros / keep C
+                t.row = it_row; t.orow = orow; t.p0 = s; t.cnt = 0; t.last = 1; t.myc = -1; t.myv = 0.f;
+                return;
+            }
+        }
+        t.row = it_row;
+        t.orow = it_orow;
+        t.p0 = it_p;
+        t.cnt = min(TMA_SLOTS, it_e - it_p);
+        it_p += t.cnt;
+        t.last = (it_p >= it_e);
+        t.myc = -1;
+        t.myv = 0.f;
+        if (lane < t.cnt) {
+            t.myc = __ldcs(a.indices + t.p0 + lane);
+            t.myv = __ldcs(a.vals + t.p0 + lane);
+        }
+    };
+    auto issue = [&](const TmaItem &t, int st) {
+        const unsigned valid = __ballot_sync(0xffffffffu, t.myc >= 0);
+        if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)__popc(valid) * row_bytes);
+        __syncwarp();
+        if (t.myc >= 0)
+            bulk_g2s(wbase + ((size_t)st * TMA_SLOTS + lane) * a.k, a.X + (long long)t.myc * a.k, row_bytes, &bars[st]);
+    };
+
+    float4 acc[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) acc[i] = f4_zero();
+
+    TmaItem cur, nxt;
+    int stage = 0;
+    next_item(cur);
+    if (cur.row >= 0) issue(cur, stage);
+    while (cur.row >= 0) {
+        next_item(nxt);
+        if (nxt.row >= 0) issue(nxt, stage ^ 1);
+        if (stage == 0) { mbar_wait(&bars[0], parity0); parity0 ^= 1u; }
+        else            { mbar_wait(&bars[1], parity1); parity1 ^= 1u; }
+        const float4 *sm4 = reinterpret_cast<const float4 *>(wbase + (size_t)stage * TMA_SLOTS * a.k);
+        for (int u = 0; u < cur.cnt; ++u) {
+            const int c = __shfl_sync(0xffffffffu, cur.myc, u);
+            const float v = __shfl_sync(0xffffffffu, cur.myv, u);
+            if (c >= 0) {
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const int vec = lane + i * 32;
+                    if (vec < k4) f4_fma(acc[i], v, sm4[(size_t)u * k4 + vec]);
+                }
+            }
+        }
+        if (cur.last) {
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                const int vec = lane + i * 32;
+                if (vec < k4) {
+                    float4 *dst = C4 + cur.orow * k4 + vec;
+                    if (ACC) {
+                        float4 old = *dst;
+                        f4_add(acc[i], old);
+                        *dst = acc[i];
+                    } else {
+                        __stcs(dst, acc[i]);
+                    }
+                }
+                acc[i] = f4_zero();
+            }
+        }
+        __syncwarp();           // every lane is done with this stage before it is refilled
+        cur = nxt;
+        stage ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic k (not a multiple of 4): warp per row, lanes over columns, scalar accesses.
+// ------------------------------------------------------------------------------------------------
+template <bool ROWMAP, bool ACC>
+__global__ void __launch_bounds__(256) k_spmm_generic(SpmmArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (long long row = warp_id; row < a.n_rows; row += warps_total) {
+        const int s = __ldg(a.indptr + row);
+        const int e = __ldg(a.indptr + row + 1);
+        if (e - s > a.long_threshold) continue;
+        long long orow = row;
+        if (ROWMAP) {
+            orow = __ldg(a.rowmap + row);
+            if (orow < 0) continue;
+        }
+        for (int c0 = 0; c0 < a.k; c0 += 128) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int p = s; p < e; ++p) {
+                const int c = __ldg(a.indices + p);
+                const float v = __ldg(a.vals + p);
+                if (c < 0) continue;
+                const float *xr = a.X + (long long)c * a.k;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int col = c0 + lane + 32 * i;
+                    if (col < a.k) acc[i] = fmaf(v, __ldg(xr + col), acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = c0 + lane + 32 * i;
+                if (col < a.k) {
+                    float *dst = a.C + orow * a.k + col;
+                    *dst = ACC ? (*dst + acc[i]) : acc[i];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// long rows (hubs of the arrow head): one CTA per segment of `segment` non-zeros, partial sums to
+// scratch, then an in-order reduction per row -- deterministic, no atomics.
+// ------------------------------------------------------------------------------------------------
+struct LongArgs {
+    const LongTask *__restrict__ tasks;
+    const int *__restrict__ indices;
+    const float *__restrict__ vals;
+    const float *__restrict__ X;
+    float *__restrict__ scratch;      // [slot][k]
+    int k;
+};
+
+__global__ void __launch_bounds__(256) k_spmm_long_partial(LongArgs a) {
+    extern __shared__ float red[];    // [warps][k]
+    const LongTask t = a.tasks[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int c0 = 0; c0 < a.k; c0 += 128) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int p = t.begin + warp; p < t.end; p += nwarps) {
+            const int c = __ldg(a.indices + p);
+            const float v = __ldg(a.vals + p);
+            if (c < 0) continue;
+            const float *xr = a.X + (long long)c * a.k;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = c0 + lane + 32 * i;
+                if (col < a.k) acc[i] = fmaf(v, __ldg(xr + col), acc[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int col = c0 + lane + 32 * i;
+            if (col < a.k) red[warp * a.k + col] = acc[i];
+        }
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < a.k; col += blockDim.x) {
+        float sum = 0.f;
+        for (int w = 0; w < nwarps; ++w) sum += red[w * a.k + col];
+        a.scratch[(long long)t.slot * a.k + col] = sum;
+    }
+}
+
+template <bool ROWMAP, bool ACC>
+__global__ void __launch_bounds__(128) k_spmm_long_reduce(const int *__restrict__ long_rows,
+                                                          const int *__restrict__ long_first,
+                                                          const float *__restrict__ scratch,
+                                                          float *__restrict__ C, const int *__restrict__ rowmap, int k) {
+    const int r = long_rows[blockIdx.x];
+    long long orow = r;
+    if (ROWMAP) {
+        orow = rowmap[r];
+        if (orow < 0) return;
+    }
+    const int s0 = long_first[blockIdx.x], s1 = long_first[blockIdx.x + 1];
+    for (int col = threadIdx.x; col < k; col += blockDim.x) {
+        float sum = 0.f;
+        for (int s = s0; s < s1; ++s) sum += scratch[(long long)s * k + col];
+        float *dst = C + orow * k + col;
+        *dst = ACC ? (*dst + sum) : sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exchange kernels: dst[r] (+)= src[map[r]]
+// ------------------------------------------------------------------------------------------------
+constexpr int MAX_SRC = 16;
+struct MultiSrc {
+    const float *p[MAX_SRC];
+    long long bound[MAX_SRC + 1];
+    int n;
+};
+
+template <typename VT, bool ACC, bool MULTI>
+__global__ void __launch_bounds__(256) k_gather_rows(VT *__restrict__ dst, const VT *__restrict__ src, MultiSrc ms,
+                                                     const int *__restrict__ map, long long n_rows, int vec_per_row) {
+    const long long total = n_rows * vec_per_row;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const long long r = t / vec_per_row;
+        const int v = (int)(t - r * vec_per_row);
+        const int m = __ldg(map + r);
+        if (m < 0) continue;
+        VT val;
+        if (MULTI) {
+            int s = 0;
+#pragma unroll 1
+            while (s + 1 < ms.n && (long long)m >= ms.bound[s + 1]) ++s;
+            const VT *sp = reinterpret_cast<const VT *>(ms.p[s]);
+            val = sp[((long long)m - ms.bound[s]) * vec_per_row + v];
+        } else {
+            val = __ldg(src + (long long)m * vec_per_row + v);
+        }
+        VT *d = dst + t;
+        if (ACC) {
+            VT old = *d;
+            if constexpr (sizeof(VT) == 16) {
+                f4_add(val, old);
+            } else {
+                val += old;
+            }
+        }
+        *d = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_fill(T *p, T v, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+template <typename SrcT>
+__global__ void k_to_i32(const SrcT *__restrict__ in, int *__restrict__ out, long long n, long long base, int *bad) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long v = (long long)in[i] - base;
+        if (v < 0 || v > 2147483647LL) atomicExch(bad, 1);
+        out[i] = (int)v;
+    }
+}
+
+__global__ void k_map_from_i64(const long long *__restrict__ in, int *__restrict__ out, long long n, long long limit) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long v = in[i];
+        out[i] = (v < 0 || v >= limit) ? -1 : (int)v;
+    }
+}
+
+__global__ void k_remap(const int *__restrict__ idx, const int *__restrict__ map, long long map_n, int *__restrict__ out,
+                        long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = idx[i];
+        out[i] = (c < 0 || c >= map_n) ? -1 : map[c];
+    }
+}
+
+__global__ void k_map_invert(const int *__restrict__ map, long long n, int *__restrict__ out, long long n_out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int q = map[i];
+        if (q >= 0 && q < n_out) out[q] = (int)i;
+    }
+}
+
+// Cross-GPU barrier over peer-mapped flag words: rank r writes `epoch` into slot r of every peer's
+// flag array, then waits until every slot of its own array reached `epoch`.
+struct PeerFlags {
+    unsigned int *p[MAX_SRC];
+};
+__global__ void k_peer_barrier(PeerFlags flags, int rank, int world, unsigned int epoch, int *status) {
+    __threadfence_system();
+    const int s = threadIdx.x;
+    if (s < world) {
+        volatile unsigned int *remote = flags.p[s] + rank;
+        *remote = epoch;
+        __threadfence_system();
+        volatile unsigned int *mine = flags.p[rank] + s;
+        const long long t0 = clock64();
+        while ((int)(*mine - epoch) < 0) {
+            if (clock64() - t0 > 8000000000LL) {      // ~4 s at 2 GHz: give up instead of hanging the box
+                atomicExch(status, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+int grid_for(arrow_ctx *ctx, const void *fn, int threads, size_t smem, long long work_ctas) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+    long long resident = (long long)occ * ctx->sm_count;
+    long long g = std::min<long long>(std::max<long long>(work_ctas, 1), resident);
+    return (int)g;
+}
+
+template <int G, int VPL>
+int launch_vec(arrow_ctx *ctx, const SpmmArgs &a, bool rowmap, bool acc, int variant) {
+    constexpr int RPW = 32 / G;
+    const int threads = 256;
+    const long long rows_per_cta = (long long)(threads / 32) * RPW;
+    const long long ctas = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
+#define LAUNCH_K(KERNEL)                                                                              \
+    do {                                                                                              \
+        auto fn = KERNEL;                                                                             \
+        int grid = grid_for(ctx, (const void *)fn, threads, 0, ctas);                                 \
+        fn<<<grid, threads, 0, ctx->stream>>>(a);                                                     \
+    } while (0)
+    if (variant == ARROW_VARIANT_SHFL) {
+        if (rowmap && acc) LAUNCH_K((k_spmm_shfl<G, VPL, true, true>));
+        else if (rowmap) LAUNCH_K((k_spmm_shfl<G, VPL, true, false>));
+        else if (acc) LAUNCH_K((k_spmm_shfl<G, VPL, false, true>));
+        else LAUNCH_K((k_spmm_shfl<G, VPL, false, false>));
+    } else {
+        if (rowmap && acc) LAUNCH_K((k_spmm_direct<G, VPL, true, true>));
+        else if (rowmap) LAUNCH_K((k_spmm_direct<G, VPL, true, false>));
+        else if (acc) LAUNCH_K((k_spmm_direct<G, VPL, false, true>));
+        else LAUNCH_K((k_spmm_direct<G, VPL, false, false>));
+    }
+#undef LAUNCH_K
+    ctx->launches++;
+    return ARROW_OK;
+}
+
+template <int VPL>
+int launch_tma(arrow_ctx *ctx, const SpmmArgs &a, bool rowmap, bool acc) {
+    const int threads = TMA_WARPS * 32;
+    const size_t smem = (size_t)TMA_WARPS * TMA_STAGES * TMA_SLOTS * a.k * 4 + TMA_WARPS * TMA_STAGES * 8;
+    const long long ctas = (a.n_rows + TMA_WARPS - 1) / TMA_WARPS;
+#define LAUNCH_T(KERNEL)                                                                              \
+    do {                                                                                              \
+        auto fn = KERNEL;                                                                             \
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+        int grid = grid_for(ctx, (const void *)fn, threads, smem, ctas);                              \
+        fn<<<grid, threads, smem, ctx->stream>>>(a);                                                  \
+    } while (0)
+    if (rowmap && acc) LAUNCH_T((k_spmm_tma<VPL, true, true>));
+    else if (rowmap) LAUNCH_T((k_spmm_tma<VPL, true, false>));
+    else if (acc) LAUNCH_T((k_spmm_tma<VPL, false, true>));
+    else LAUNCH_T((k_spmm_tma<VPL, false, false>));
+#undef LAUNCH_T
+    ctx->launches++;
+    return ARROW_OK;
+}
+
+int pick_variant(int k) {
+    (void)k;
+    return ARROW_VARIANT_SHFL;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int arrow_b200_abi_version(void) { return ARROW_ABI_VERSION; }
+
+const char *arrow_last_error(const arrow_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int arrow_ctx_create(int device, void *stream, arrow_ctx **out) {
+    if (!out) return fail(nullptr, ARROW_ERR_ARG, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, ARROW_ERR_CUDA, "no CUDA device available (%s); libarrow_b200 has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, ARROW_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, ARROW_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    arrow_ctx *ctx = new arrow_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, ARROW_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            delete ctx;
+            return fail(nullptr, ARROW_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        }
+        ctx->own_stream = true;
+    }
+    e = cudaMalloc(&ctx->dev_status, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(ctx->dev_status, 0, sizeof(int));
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, ARROW_ERR_CUDA, "status alloc: %s", cudaGetErrorString(e));
+    }
+    *out = ctx;
+    return ARROW_OK;
+}
+
+void arrow_ctx_destroy(arrow_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &d : ctx->dense)
+        if (d.live) {
+            if (d.owned) cudaFree(d.p);
+            else if (d.ipc) cudaIpcCloseMemHandle(d.p);
+        }
+    for (auto &c : ctx->csrs)
+        if (c.live) {
+            if (c.owns_indptr) cudaFree(c.indptr);
+            if (c.owns_indices) cudaFree(c.indices);
+            if (c.owns_vals) cudaFree(c.vals);
+            if (c.owns_long) {
+                cudaFree(c.long_tasks);
+                cudaFree(c.long_rows);
+                cudaFree(c.long_first);
+            }
+        }
+    for (auto &m : ctx->maps)
+        if (m.live) cudaFree(m.p);
+    for (auto &t : ctx->timers) {
+        if (t.a) cudaEventDestroy(t.a);
+        if (t.b) cudaEventDestroy(t.b);
+    }
+    if (ctx->long_scratch) cudaFree(ctx->long_scratch);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->dev_status) cudaFree(ctx->dev_status);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int arrow_sync(arrow_ctx *ctx) {
+    CHECK_CTX(ctx);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int st = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&st, ctx->dev_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != 0) {
+        cudaMemset(ctx->dev_status, 0, sizeof(int));
+        return fail(ctx, ARROW_ERR_CUDA, "device-side failure flag %d (peer barrier timed out)", st);
+    }
+    return ARROW_OK;
+}
+
+int arrow_device_info(arrow_ctx *ctx, int *sm_count, int64_t *free_bytes, int64_t *total_bytes) {
+    CHECK_CTX(ctx);
+    size_t f = 0, t = 0;
+    CUDA_TRY(ctx, cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return ARROW_OK;
+}
+
+int arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segment) {
+    CHECK_CTX(ctx);
+    if (long_row_threshold < 1 || long_row_segment < 32) return fail(ctx, ARROW_ERR_ARG, "bad tuning values");
+    ctx->long_threshold = long_row_threshold;
+    ctx->long_segment = long_row_segment;
+    return ARROW_OK;
+}
+
+// ---- sparse -------------------------------------------------------------------------------------
+static int build_long_rows(arrow_ctx *ctx, Csr &c, const std::vector<int> &h_indptr) {
+    // host pass over the (rebased) row pointer: rows above the threshold become segment tasks
+    std::vector<LongTask> tasks;
+    std::vector<int> rows, first;
+    int64_t mx = 0;
+    const int thr = ctx->long_threshold, seg = ctx->long_segment;
+    for (int64_t r = 0; r < c.n_rows; ++r) {
+        const int len = h_indptr[r + 1] - h_indptr[r];
+        mx = std::max<int64_t>(mx, len);
+        if (len > thr) {
+            rows.push_back((int)r);
+            first.push_back((int)tasks.size());
+            for (int b = h_indptr[r]; b < h_indptr[r + 1]; b += seg)
+                tasks.push_back(LongTask{(int)r, b, std::min(b + seg, h_indptr[r + 1]), (int)tasks.size()});
+        }
+    }
+    first.push_back((int)tasks.size());
+    c.max_row_nnz = mx;
+    c.long_threshold = thr;
+    c.n_long_rows = (int)rows.size();
+    c.n_long_tasks = (int)tasks.size();
+    if (!rows.empty()) {
+        CUDA_TRY(ctx, cudaMalloc(&c.long_tasks, tasks.size() * sizeof(LongTask)));
+        CUDA_TRY(ctx, cudaMalloc(&c.long_rows, rows.size() * sizeof(int)));
+        CUDA_TRY(ctx, cudaMalloc(&c.long_first, first.size() * sizeof(int)));
+        c.owns_long = true;
+        CUDA_TRY(ctx, cudaMemcpy(c.long_tasks, tasks.data(), tasks.size() * sizeof(LongTask), cudaMemcpyHostToDevice));
+        CUDA_TRY(ctx, cudaMemcpy(c.long_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(ctx, cudaMemcpy(c.long_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return ARROW_OK;
+}
+
+int arrow_csr_upload(arrow_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *indptr, int indptr_bytes,
+                     const void *indices, int indices_bytes, const float *data, int *csr_out) {
+    CHECK_CTX(ctx);
+    if (!csr_out || !indptr || (nnz > 0 && !indices)) return fail(ctx, ARROW_ERR_ARG, "null pointer argument");
+    if (n_rows < 0 || n_cols < 0 || nnz < 0) return fail(ctx, ARROW_ERR_ARG, "negative size");
+    if ((indptr_bytes != 4 && indptr_bytes != 8) || (indices_bytes != 4 && indices_bytes != 8))
+        return fail(ctx, ARROW_ERR_ARG, "index width must be 4 or 8 bytes");
+    if (nnz > 2147483647LL || n_rows >= 2147483647LL || n_cols > 2147483647LL)
+        return fail(ctx, ARROW_ERR_RANGE, "block exceeds the int32 device layout (rows=%lld cols=%lld nnz=%lld); shard it",
+                    (long long)n_rows, (long long)n_cols, (long long)nnz);
+    // host view of the row pointer, rebased
+    std::vector<int> h_indptr((size_t)n_rows + 1);
+    int64_t base = 0;
+    if (indptr_bytes == 8) {
+        const int64_t *ip = (const int64_t *)indptr;
+        base = ip[0];
+        for (int64_t r = 0; r <= n_rows; ++r) {
+            const int64_t v = ip[r] - base;
+            if (v < 0 || v > nnz || (r > 0 && v < h_indptr[r - 1]))
+                return fail(ctx, ARROW_ERR_ARG, "indptr is not a non-decreasing sequence inside [0, nnz] at row %lld", (long long)r);
+            h_indptr[r] = (int)v;
+        }
+    } else {
+        const int32_t *ip = (const int32_t *)indptr;
+        base = ip[0];
+        for (int64_t r = 0; r <= n_rows; ++r) {
+            const int64_t v = (int64_t)ip[r] - base;
+            if (v < 0 || v > nnz || (r > 0 && v < h_indptr[r - 1]))
+                return fail(ctx, ARROW_ERR_ARG, "indptr is not a non-decreasing sequence inside [0, nnz] at row %lld", (long long)r);
+            h_indptr[r] = (int)v;
+        }
+    }
+    if (h_indptr[n_rows] != nnz)
+        return fail(ctx, ARROW_ERR_ARG, "indptr[n_rows]-indptr[0] = %d but nnz = %lld", h_indptr[n_rows], (long long)nnz);
+
+    Csr c;
+    c.n_rows = n_rows;
+    c.n_cols = n_cols;
+    c.nnz = nnz;
+    CUDA_TRY(ctx, cudaMalloc(&c.indptr, ((size_t)n_rows + 1) * sizeof(int)));
+    c.owns_indptr = true;
+    CUDA_TRY(ctx, cudaMemcpyAsync(c.indptr, h_indptr.data(), ((size_t)n_rows + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+    CUDA_TRY(ctx, cudaMalloc(&c.indices, nz * sizeof(int)));
+    c.owns_indices = true;
+    CUDA_TRY(ctx, cudaMalloc(&c.vals, nz * sizeof(float)));
+    c.owns_vals = true;
+    if (nnz > 0) {
+        if (indices_bytes == 4) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(c.indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            long long *tmp = nullptr;
+            int *bad = nullptr;
+            CUDA_TRY(ctx, cudaMalloc(&tmp, (size_t)nnz * 8));
+            CUDA_TRY(ctx, cudaMalloc(&bad, sizeof(int)));
+            CUDA_TRY(ctx, cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(tmp, indices, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+            k_to_i32<long long><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(tmp, c.indices, nnz, 0, bad);
+            ctx->launches++;
+            int hbad = 0;
+            CUDA_TRY(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(tmp);
+            cudaFree(bad);
+            if (hbad) return fail(ctx, ARROW_ERR_RANGE, "a column index does not fit int32");
+        }
+        if (data) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(c.vals, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            k_fill<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c.vals, 1.0f, nnz);
+            ctx->launches++;
+        }
+    }
+    int rc = build_long_rows(ctx, c, h_indptr);
+    if (rc != ARROW_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // host staging vector goes out of scope
+    CUDA_TRY(ctx, cudaGetLastError());
+    c.live = true;
+    const int h = new_slot(ctx->csrs);
+    ctx->csrs[h] = c;
+    *csr_out = h;
+    return ARROW_OK;
+}
+
+int arrow_csr_free(arrow_ctx *ctx, int csr) {
+    CHECK_CTX(ctx);
+    Csr *c = get_csr(ctx, csr);
+    if (!c) return fail(ctx, ARROW_ERR_HANDLE, "bad csr handle %d", csr);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (c->owns_indptr) cudaFree(c->indptr);
+    if (c->owns_indices) cudaFree(c->indices);
+    if (c->owns_vals) cudaFree(c->vals);
+    if (c->owns_long) {
+        cudaFree(c->long_tasks);
+        cudaFree(c->long_rows);
+        cudaFree(c->long_first);
+    }
+    *c = Csr();
+    return ARROW_OK;
+}
+
+int arrow_csr_info(arrow_ctx *ctx, int csr, int64_t *n_rows, int64_t *n_cols, int64_t *nnz, int64_t *max_row_nnz,
+                   int64_t *n_long_rows) {
+    CHECK_CTX(ctx);
+    Csr *c = get_csr(ctx, csr);
+    if (!c) return fail(ctx, ARROW_ERR_HANDLE, "bad csr handle %d", csr);
+    if (n_rows) *n_rows = c->n_rows;
+    if (n_cols) *n_cols = c->n_cols;
+    if (nnz) *nnz = c->nnz;
+    if (max_row_nnz) *max_row_nnz = c->max_row_nnz;
+    if (n_long_rows) *n_long_rows = c->n_long_rows;
+    return ARROW_OK;
+}
+
+int arrow_csr_remap_columns(arrow_ctx *ctx, int csr, int map, int64_t new_n_cols, int *csr_out) {
+    CHECK_CTX(ctx);
+    Csr *c = get_csr(ctx, csr);
+    IdxMap *m = get_map(ctx, map);
+    if (!c) return fail(ctx, ARROW_ERR_HANDLE, "bad csr handle %d", csr);
+    if (!m) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle %d", map);
+    if (!csr_out) return fail(ctx, ARROW_ERR_ARG, "csr_out is null");
+    Csr d = *c;
+    d.owns_indptr = d.owns_vals = d.owns_long = false;      // shared with the source block
+    d.owns_indices = true;
+    d.indices = nullptr;
+    d.n_cols = new_n_cols;
+    d.may_skip = true;
+    CUDA_TRY(ctx, cudaMalloc(&d.indices, (size_t)std::max<int64_t>(c->nnz, 1) * sizeof(int)));
+    if (c->nnz > 0) {
+        k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->indices, m->p, m->n, d.indices, c->nnz);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    const int h = new_slot(ctx->csrs);
+    ctx->csrs[h] = d;
+    *csr_out = h;
+    return ARROW_OK;
+}
+
+// ---- maps ---------------------------------------------------------------------------------------
+int arrow_map_upload(arrow_ctx *ctx, const int64_t *map, int64_t n, int64_t limit, int *map_out) {
+    CHECK_CTX(ctx);
+    if (!map_out || (n > 0 && !map)) return fail(ctx, ARROW_ERR_ARG, "null pointer argument");
+    if (n < 0 || limit < 0 || limit > 2147483647LL || n > 2147483647LL)
+        return fail(ctx, ARROW_ERR_RANGE, "map size/limit exceed the int32 device layout");
+    IdxMap m;
+    m.n = n;
+    m.limit = limit;
+    CUDA_TRY(ctx, cudaMalloc(&m.p, (size_t)std::max<int64_t>(n, 1) * sizeof(int)));
+    if (n > 0) {
+        long long *tmp = nullptr;
+        CUDA_TRY(ctx, cudaMalloc(&tmp, (size_t)n * 8));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp, map, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        k_map_from_i64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(tmp, m.p, n, limit);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmp);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    m.live = true;
+    const int h = new_slot(ctx->maps);
+    ctx->maps[h] = m;
+    *map_out = h;
+    return ARROW_OK;
+}
+
+int arrow_map_free(arrow_ctx *ctx, int map) {
+    CHECK_CTX(ctx);
+    IdxMap *m = get_map(ctx, map);
+    if (!m) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle %d", map);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(m->p);
+    *m = IdxMap();
+    return ARROW_OK;
+}
+
+int arrow_map_compose(arrow_ctx *ctx, int inner, int outer, int *map_out) {
+    CHECK_CTX(ctx);
+    IdxMap *a = get_map(ctx, inner), *b = get_map(ctx, outer);
+    if (!a || !b) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle");
+    if (!map_out) return fail(ctx, ARROW_ERR_ARG, "map_out is null");
+    IdxMap m;
+    m.n = a->n;
+    m.limit = b->limit;
+    CUDA_TRY(ctx, cudaMalloc(&m.p, (size_t)std::max<int64_t>(m.n, 1) * sizeof(int)));
+    if (m.n > 0) {
+        k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a->p, b->p, b->n, m.p, m.n);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    m.live = true;
+    const int h = new_slot(ctx->maps);
+    ctx->maps[h] = m;
+    *map_out = h;
+    return ARROW_OK;
+}
+
+int arrow_map_invert(arrow_ctx *ctx, int map, int64_t n_out, int *map_out) {
+    CHECK_CTX(ctx);
+    IdxMap *a = get_map(ctx, map);
+    if (!a) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle %d", map);
+    if (!map_out || n_out < 0 || n_out > 2147483647LL) return fail(ctx, ARROW_ERR_ARG, "bad argument");
+    IdxMap m;
+    m.n = n_out;
+    m.limit = a->n;
+    CUDA_TRY(ctx, cudaMalloc(&m.p, (size_t)std::max<int64_t>(n_out, 1) * sizeof(int)));
+    if (n_out > 0) {
+        k_fill<int><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m.p, -1, n_out);
+        ctx->launches++;
+    }
+    if (a->n > 0) {
+        k_map_invert<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a->p, a->n, m.p, n_out);
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    m.live = true;
+    const int h = new_slot(ctx->maps);
+    ctx->maps[h] = m;
+    *map_out = h;
+    return ARROW_OK;
+}
+
+int arrow_map_d2h(arrow_ctx *ctx, int map, int32_t *host, int64_t n) {
+    CHECK_CTX(ctx);
+    IdxMap *a = get_map(ctx, map);
+    if (!a) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle %d", map);
+    if (!host || n < 0 || n > a->n) return fail(ctx, ARROW_ERR_ARG, "bad host buffer / length");
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, a->p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ARROW_OK;
+}
+
+// ---- dense --------------------------------------------------------------------------------------
+int arrow_dense_alloc(arrow_ctx *ctx, int64_t rows, int k, int *buf_out) {
+    CHECK_CTX(ctx);
+    if (!buf_out || rows < 0 || k < 1) return fail(ctx, ARROW_ERR_ARG, "bad dense shape %lld x %d", (long long)rows, k);
+    DenseBuf d;
+    d.rows = rows;
+    d.k = k;
+    const size_t bytes = std::max<size_t>((size_t)rows * (size_t)k * 4, 16);
+    cudaError_t e = cudaMalloc(&d.p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, ARROW_ERR_NOMEM, "cudaMalloc(%zu bytes) for a %lld x %d tile: %s", bytes, (long long)rows, k,
+                    cudaGetErrorString(e));
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(d.p, 0, bytes, ctx->stream));
+    d.owned = true;
+    d.live = true;
+    const int h = new_slot(ctx->dense);
+    ctx->dense[h] = d;
+    *buf_out = h;
+    return ARROW_OK;
+}
+
+int arrow_dense_free(arrow_ctx *ctx, int buf) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (d->owned) cudaFree(d->p);
+    else if (d->ipc) cudaIpcCloseMemHandle(d->p);
+    *d = DenseBuf();
+    return ARROW_OK;
+}
+
+int arrow_dense_fill(arrow_ctx *ctx, int buf, float value) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
+    const long long n = (long long)d->rows * d->k;
+    if (n == 0) return ARROW_OK;
+    if (value == 0.f) {
+        CUDA_TRY(ctx, cudaMemsetAsync(d->p, 0, (size_t)n * 4, ctx->stream));
+    } else {
+        k_fill<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d->p, value, n);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return ARROW_OK;
+}
+
+int arrow_dense_h2d(arrow_ctx *ctx, int buf, int64_t row0, int64_t rows, const float *host) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
+    if (!host || row0 < 0 || rows < 0 || row0 + rows > d->rows)
+        return fail(ctx, ARROW_ERR_ARG, "h2d rows [%lld,%lld) outside tile of %lld rows", (long long)row0, (long long)(row0 + rows), (long long)d->rows);
+    if (rows == 0) return ARROW_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d->p + (size_t)row0 * d->k, host, (size_t)rows * d->k * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return ARROW_OK;
+}
+
+int arrow_dense_d2h(arrow_ctx *ctx, int buf, int64_t row0, int64_t rows, float *host) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
+    if (!host || row0 < 0 || rows < 0 || row0 + rows > d->rows)
+        return fail(ctx, ARROW_ERR_ARG, "d2h rows [%lld,%lld) outside tile of %lld rows", (long long)row0, (long long)(row0 + rows), (long long)d->rows);
+    if (rows == 0) return ARROW_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, d->p + (size_t)row0 * d->k, (size_t)rows * d->k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return ARROW_OK;
+}
+
+int arrow_dense_copy(arrow_ctx *ctx, int dst, int64_t dst_row0, int src, int64_t src_row0, int64_t rows) {
+    CHECK_CTX(ctx);
+    DenseBuf *a = get_dense(ctx, dst), *b = get_dense(ctx, src);
+    if (!a || !b) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle");
+    if (a->k != b->k) return fail(ctx, ARROW_ERR_ARG, "feature width mismatch %d vs %d", a->k, b->k);
+    if (rows < 0 || dst_row0 < 0 || src_row0 < 0 || dst_row0 + rows > a->rows || src_row0 + rows > b->rows)
+        return fail(ctx, ARROW_ERR_ARG, "copy range outside tiles");
+    if (rows == 0) return ARROW_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(a->p + (size_t)dst_row0 * a->k, b->p + (size_t)src_row0 * b->k, (size_t)rows * a->k * 4,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    return ARROW_OK;
+}
+
+int arrow_dense_ptr(arrow_ctx *ctx, int buf, void **device_ptr, int64_t *rows, int *k) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
+    if (device_ptr) *device_ptr = d->p;
+    if (rows) *rows = d->rows;
+    if (k) *k = d->k;
+    return ARROW_OK;
+}
+
+int arrow_dense_wrap(arrow_ctx *ctx, void *device_ptr, int64_t rows, int k, int *buf_out) {
+    CHECK_CTX(ctx);
+    if (!device_ptr || !buf_out || rows < 0 || k < 1) return fail(ctx, ARROW_ERR_ARG, "bad wrap arguments");
+    DenseBuf d;
+    d.p = (float *)device_ptr;
+    d.rows = rows;
+    d.k = k;
+    d.live = true;
+    const int h = new_slot(ctx->dense);
+    ctx->dense[h] = d;
+    *buf_out = h;
+    return ARROW_OK;
+}
+
+int arrow_host_alloc(size_t bytes, void **ptr) {
+    if (!ptr) return ARROW_ERR_ARG;
+    cudaError_t e = cudaMallocHost(ptr, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, ARROW_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return ARROW_OK;
+}
+
+int arrow_host_free(void *ptr) {
+    if (!ptr) return ARROW_OK;
+    return cudaFreeHost(ptr) == cudaSuccess ? ARROW_OK : ARROW_ERR_CUDA;
+}
+
+// ---- hot path -----------------------------------------------------------------------------------
+int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int flags, int variant) {
+    CHECK_CTX(ctx);
+    Csr *A = get_csr(ctx, csr);
+    DenseBuf *X = get_dense(ctx, x_buf), *C = get_dense(ctx, c_buf);
+    if (!A) return fail(ctx, ARROW_ERR_HANDLE, "bad csr handle %d", csr);
+    if (!X || !C) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle (x=%d c=%d)", x_buf, c_buf);
+    if (X->k != C->k) return fail(ctx, ARROW_ERR_ARG, "X has %d feature columns, C has %d", X->k, C->k);
+    if (X->p == C->p) return fail(ctx, ARROW_ERR_ARG, "X and C must not alias");
+    if (X->rows < A->n_cols) return fail(ctx, ARROW_ERR_ARG, "X has %lld rows, block has %lld columns", (long long)X->rows, (long long)A->n_cols);
+    IdxMap *rm = nullptr;
+    if (rowmap >= 0) {
+        rm = get_map(ctx, rowmap);
+        if (!rm) return fail(ctx, ARROW_ERR_HANDLE, "bad rowmap handle %d", rowmap);
+        if (rm->n < A->n_rows) return fail(ctx, ARROW_ERR_ARG, "rowmap has %lld entries, block has %lld rows", (long long)rm->n, (long long)A->n_rows);
+        if (rm->limit > C->rows) return fail(ctx, ARROW_ERR_ARG, "rowmap reaches row %lld, C has %lld rows", (long long)rm->limit, (long long)C->rows);
+    } else if (C->rows < A->n_rows) {
+        return fail(ctx, ARROW_ERR_ARG, "C has %lld rows, block has %lld rows", (long long)C->rows, (long long)A->n_rows);
+    }
+    if (A->n_rows == 0) return ARROW_OK;
+    const bool acc = (flags & ARROW_ACCUMULATE) != 0;
+    const int k = X->k;
+    SpmmArgs a;
+    a.indptr = A->indptr;
+    a.indices = A->indices;
+    a.vals = A->vals;
+    a.X = X->p;
+    a.C = C->p;
+    a.rowmap = rm ? rm->p : nullptr;
+    a.n_rows = A->n_rows;
+    a.k = k;
+    a.k4 = k / 4;
+    a.long_threshold = A->long_threshold;
+    if (variant == ARROW_VARIANT_AUTO) variant = pick_variant(k);
+    if (variant < 0 || variant > 2) return fail(ctx, ARROW_ERR_ARG, "unknown variant %d", variant);
+
+    const bool vec_ok = (k % 4 == 0) && k <= 256;
+    if (!vec_ok) {
+        const long long ctas = (A->n_rows + 7) / 8;
+#define LAUNCH_G(KERNEL)                                                                              \
+    do {                                                                                              \
+        auto fn = KERNEL;                                                                             \
+        int grid = grid_for(ctx, (const void *)fn, 256, 0, ctas);                                     \
+        fn<<<grid, 256, 0, ctx->stream>>>(a);                                                         \
+    } while (0)
+        if (rm && acc) LAUNCH_G((k_spmm_generic<true, true>));
+        else if (rm) LAUNCH_G((k_spmm_generic<true, false>));
+        else if (acc) LAUNCH_G((k_spmm_generic<false, true>));
+        else LAUNCH_G((k_spmm_generic<false, false>));
+#undef LAUNCH_G
+        ctx->launches++;
+    } else if (variant == ARROW_VARIANT_TMA && k >= 32) {
+        if (a.k4 <= 32) launch_tma<1>(ctx, a, rm != nullptr, acc);
+        else launch_tma<2>(ctx, a, rm != nullptr, acc);
+    } else {
+        if (variant == ARROW_VARIANT_TMA) variant = ARROW_VARIANT_SHFL;
+        const int k4 = a.k4;
+        if (k4 <= 1) launch_vec<1, 1>(ctx, a, rm != nullptr, acc, variant);
+        else if (k4 <= 2) launch_vec<2, 1>(ctx, a, rm != nullptr, acc, variant);
+        else if (k4 <= 4) launch_vec<4, 1>(ctx, a, rm != nullptr, acc, variant);
+        else if (k4 <= 8) launch_vec<8, 1>(ctx, a, rm != nullptr, acc, variant);
+        else if (k4 <= 16) launch_vec<16, 1>(ctx, a, rm != nullptr, acc, variant);
+        else if (k4 <= 32) launch_vec<32, 1>(ctx, a, rm != nullptr, acc, variant);
+        else launch_vec<32, 2>(ctx, a, rm != nullptr, acc, variant);
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+
+    if (A->n_long_tasks > 0) {
+        const size_t need = (size_t)A->n_long_tasks * k * 4;
+        if (need > ctx->long_scratch_bytes) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->long_scratch) cudaFree(ctx->long_scratch);
+            ctx->long_scratch = nullptr;
+            ctx->long_scratch_bytes = 0;
+            CUDA_TRY(ctx, cudaMalloc(&ctx->long_scratch, need));
+            ctx->long_scratch_bytes = need;
+        }
+        LongArgs la;
+        la.tasks = A->long_tasks;
+        la.indices = A->indices;
+        la.vals = A->vals;
+        la.X = X->p;
+        la.scratch = ctx->long_scratch;
+        la.k = k;
+        const size_t smem = (size_t)8 * k * 4;
+        if (smem > 48 * 1024)
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k_spmm_long_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_spmm_long_partial<<<A->n_long_tasks, 256, smem, ctx->stream>>>(la);
+        ctx->launches++;
+        const int *rmp = rm ? rm->p : nullptr;
+        if (rm && acc) k_spmm_long_reduce<true, true><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
+        else if (rm) k_spmm_long_reduce<true, false><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
+        else if (acc) k_spmm_long_reduce<false, true><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
+        else k_spmm_long_reduce<false, false><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    return ARROW_OK;
+}
+
+static int gather_common(arrow_ctx *ctx, DenseBuf *D, const float *src, const MultiSrc &ms, bool multi, IdxMap *m, bool acc) {
+    const long long n_rows = m->n;
+    if (n_rows == 0) return ARROW_OK;
+    const int k = D->k;
+    const bool vec = (k % 4 == 0);
+    const int vpr = vec ? k / 4 : k;
+    const long long total = n_rows * vpr;
+    const int threads = 256;
+    int grid = (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 16);
+    grid = std::max(grid, 1);
+#define LAUNCH_GA(VT, ACCV, MULTIV)                                                                              \
+    k_gather_rows<VT, ACCV, MULTIV><<<grid, threads, 0, ctx->stream>>>(reinterpret_cast<VT *>(D->p),            \
+                                                                      reinterpret_cast<const VT *>(src), ms, m->p, n_rows, vpr)
+    if (vec) {
+        if (multi) { if (acc) LAUNCH_GA(float4, true, true); else LAUNCH_GA(float4, false, true); }
+        else       { if (acc) LAUNCH_GA(float4, true, false); else LAUNCH_GA(float4, false, false); }
+    } else {
+        if (multi) { if (acc) LAUNCH_GA(float, true, true); else LAUNCH_GA(float, false, true); }
+        else       { if (acc) LAUNCH_GA(float, true, false); else LAUNCH_GA(float, false, false); }
+    }
+#undef LAUNCH_GA
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return ARROW_OK;
+}
+
+int arrow_gather_rows(arrow_ctx *ctx, int dst_buf, int src_buf, int map, int flags) {
+    CHECK_CTX(ctx);
+    DenseBuf *D = get_dense(ctx, dst_buf), *S = get_dense(ctx, src_buf);
+    IdxMap *m = get_map(ctx, map);
+    if (!D || !S) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle (dst=%d src=%d)", dst_buf, src_buf);
+    if (!m) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle %d", map);
+    if (D->k != S->k) return fail(ctx, ARROW_ERR_ARG, "feature width mismatch %d vs %d", D->k, S->k);
+    if (D->p == S->p) return fail(ctx, ARROW_ERR_ARG, "gather source and destination must not alias");
+    if (m->n > D->rows) return fail(ctx, ARROW_ERR_ARG, "map has %lld entries, destination has %lld rows", (long long)m->n, (long long)D->rows);
+    if (m->limit > S->rows) return fail(ctx, ARROW_ERR_ARG, "map reaches row %lld, source has %lld rows", (long long)m->limit, (long long)S->rows);
+    MultiSrc ms;
+    memset(&ms, 0, sizeof ms);
+    return gather_common(ctx, D, S->p, ms, false, m, (flags & ARROW_ACCUMULATE) != 0);
+}
+
+int arrow_gather_rows_multi(arrow_ctx *ctx, int dst_buf, const int *src_bufs, const int64_t *row_bounds, int n_src, int map, int flags) {
+    CHECK_CTX(ctx);
+    DenseBuf *D = get_dense(ctx, dst_buf);
+    IdxMap *m = get_map(ctx, map);
+    if (!D) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", dst_buf);
+    if (!m) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle %d", map);
+    if (!src_bufs || !row_bounds || n_src < 1 || n_src > MAX_SRC) return fail(ctx, ARROW_ERR_ARG, "need 1..%d sources", MAX_SRC);
+    if (m->n > D->rows) return fail(ctx, ARROW_ERR_ARG, "map has %lld entries, destination has %lld rows", (long long)m->n, (long long)D->rows);
+    MultiSrc ms;
+    memset(&ms, 0, sizeof ms);
+    ms.n = n_src;
+    for (int s = 0; s < n_src; ++s) {
+        DenseBuf *S = get_dense(ctx, src_bufs[s]);
+        if (!S) return fail(ctx, ARROW_ERR_HANDLE, "bad source handle %d", src_bufs[s]);
+        if (S->k != D->k) return fail(ctx, ARROW_ERR_ARG, "feature width mismatch in source %d", s);
+        if (row_bounds[s + 1] < row_bounds[s] || row_bounds[s + 1] - row_bounds[s] > S->rows)
+            return fail(ctx, ARROW_ERR_ARG, "source %d owns %lld rows but its tile has %lld", s, (long long)(row_bounds[s + 1] - row_bounds[s]), (long long)S->rows);
+        if (S->p == D->p) return fail(ctx, ARROW_ERR_ARG, "gather source and destination must not alias");
+        ms.p[s] = S->p;
+        ms.bound[s] = row_bounds[s];
+    }
+    ms.bound[n_src] = row_bounds[n_src];
+    if (m->limit > row_bounds[n_src]) return fail(ctx, ARROW_ERR_ARG, "map reaches row %lld beyond the last source bound %lld", (long long)m->limit, (long long)row_bounds[n_src]);
+    return gather_common(ctx, D, nullptr, ms, true, m, (flags & ARROW_ACCUMULATE) != 0);
+}
+
+// ---- IPC / peer barrier -------------------------------------------------------------------------
+int arrow_ipc_export(arrow_ctx *ctx, int buf, void *handle64) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d || !d->owned) return fail(ctx, ARROW_ERR_HANDLE, "ipc export needs a tile this context allocated (handle %d)", buf);
+    static_assert(sizeof(cudaIpcMemHandle_t) == ARROW_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, d->p));
+    memcpy(handle64, &h, sizeof h);
+    return ARROW_OK;
+}
+
+int arrow_ipc_import(arrow_ctx *ctx, const void *handle64, int64_t rows, int k, int *buf_out) {
+    CHECK_CTX(ctx);
+    if (!handle64 || !buf_out || rows < 0 || k < 1) return fail(ctx, ARROW_ERR_ARG, "bad ipc import arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void *p = nullptr;
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    DenseBuf d;
+    d.p = (float *)p;
+    d.rows = rows;
+    d.k = k;
+    d.ipc = true;
+    d.live = true;
+    const int hh = new_slot(ctx->dense);
+    ctx->dense[hh] = d;
+    *buf_out = hh;
+    return ARROW_OK;
+}
+
+int arrow_peer_barrier(arrow_ctx *ctx, const int *flag_bufs, int rank, int world) {
+    CHECK_CTX(ctx);
+    if (!flag_bufs || world < 1 || world > MAX_SRC || rank < 0 || rank >= world) return fail(ctx, ARROW_ERR_ARG, "bad barrier arguments");
+    PeerFlags pf;
+    memset(&pf, 0, sizeof pf);
+    for (int s = 0; s < world; ++s) {
+        DenseBuf *d = get_dense(ctx, flag_bufs[s]);
+        if (!d || (long long)d->rows * d->k < world) return fail(ctx, ARROW_ERR_HANDLE, "bad flag tile for rank %d", s);
+        pf.p[s] = reinterpret_cast<unsigned int *>(d->p);
+    }
+    ctx->barrier_epoch++;
+    k_peer_barrier<<<1, 32, 0, ctx->stream>>>(pf, rank, world, ctx->barrier_epoch, ctx->dev_status);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return ARROW_OK;
+}
+
+// ---- timing -------------------------------------------------------------------------------------
+int arrow_timer_start(arrow_ctx *ctx, int slot) {
+    CHECK_CTX(ctx);
+    if (slot < 0 || slot >= ARROW_MAX_TIMERS) return fail(ctx, ARROW_ERR_ARG, "timer slot %d", slot);
+    Timer &t = ctx->timers[slot];
+    if (!t.a) CUDA_TRY(ctx, cudaEventCreate(&t.a));
+    if (!t.b) CUDA_TRY(ctx, cudaEventCreate(&t.b));
+    CUDA_TRY(ctx, cudaEventRecord(t.a, ctx->stream));
+    return ARROW_OK;
+}
+
+int arrow_timer_stop(arrow_ctx *ctx, int slot) {
+    CHECK_CTX(ctx);
+    if (slot < 0 || slot >= ARROW_MAX_TIMERS || !ctx->timers[slot].b) return fail(ctx, ARROW_ERR_ARG, "timer slot %d not started", slot);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->timers[slot].b, ctx->stream));
+    return ARROW_OK;
+}
+
+int arrow_timer_elapsed_ms(arrow_ctx *ctx, int slot, float *ms) {
+    CHECK_CTX(ctx);
+    if (slot < 0 || slot >= ARROW_MAX_TIMERS || !ctx->timers[slot].b || !ms) return fail(ctx, ARROW_ERR_ARG, "timer slot %d not started", slot);
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->timers[slot].b));
+    CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->timers[slot].a, ctx->timers[slot].b));
+    return ARROW_OK;
+}
+
+int arrow_launch_count(arrow_ctx *ctx, int64_t *count) {
+    if (!ctx || !count) return ARROW_ERR_ARG;
+    *count = ctx->launches;
+    return ARROW_OK;
+}
+
+int arrow_l2_flush(arrow_ctx *ctx) {
+    CHECK_CTX(ctx);
+    const size_t bytes = (size_t)256 << 20;      // 256 MiB > 126 MB of L2
+    if (!ctx->flush_buf) {
+        CUDA_TRY(ctx, cudaMalloc(&ctx->flush_buf, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    k_fill<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((float *)ctx->flush_buf, 0.f, (long long)(ctx->flush_bytes / 4));
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    return ARROW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+/*
+ * arrow_b200.h -- C ABI of libarrow_b200.so: B200 (sm_100a) arrow-decomposed SpMM hot path.
+ *
+ * The reference (spcl/arrow-matrix) is pure Python and has no FFI of its own; this is the
+ * boundary a maintainer binds with ctypes to replace the arithmetic and the
+ * data movement of
+ *     arrow/arrow_slim_mpi.py:78-244   (_ad_spmm / _ad_spmm_gpu: three CSR x dense products)
+ *     arrow/arrow_mpi.py:177-336       (wide layout: row-tile / column-tile products)
+ *     arrow/common/sp2cp.py:6-16       (_sp2cp: per-iteration CSR upload -> upload once)
+ *     arrow/arrow_dec_mpi.py:404-440   (backward exchange: C_{j-1}[to_prev[r]] += C_j[r])
+ *     arrow/arrow_dec_mpi.py:507-550   (forward exchange:  X_j[r] = X_{j-1}[to_prev[r]])
+ *
+ * Conventions: extern "C", opaque context, int return codes (0 = ok, negative = error, text via
+ * arrow_last_error), no exceptions cross the boundary.  The caller owns host memory; the library
+ * owns device memory (handles are small non-negative ints, valid for one context).  All work is
+ * stream-ordered on the context's stream; arrow_sync() waits for it.  One host thread per context.
+ * Dense tiles are row-major fp32 [rows x k]; CSR is fp32 values with int32 indices on the device.
+ */
+#ifndef ARROW_B200_H
+#define ARROW_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct arrow_ctx arrow_ctx;
+
+#define ARROW_ABI_VERSION 1
+
+/* error codes */
+#define ARROW_OK              0
+#define ARROW_ERR_CUDA       -1
+#define ARROW_ERR_ARG        -2
+#define ARROW_ERR_HANDLE     -3
+#define ARROW_ERR_RANGE      -4   /* index / size exceeds the int32 device layout */
+#define ARROW_ERR_NOMEM      -5
+#define ARROW_ERR_UNSUPPORTED -6
+
+/* flags for arrow_spmm / arrow_gather_rows */
+#define ARROW_ACCUMULATE      1   /* C += ... instead of C = ...  (reference: `C_i += A_i0 @ X_0`,
+                                     arrow_slim_mpi.py:142-144; scatter-add, arrow_dec_mpi.py:437) */
+
+/* SpMM kernel variants (arrow_spmm `variant`); ARROW_VARIANT_AUTO picks per k. */
+#define ARROW_VARIANT_AUTO    -1
+#define ARROW_VARIANT_DIRECT   0  /* sub-warp per row, broadcast index loads, float4 X gathers          */
+#define ARROW_VARIANT_SHFL     1  /* sub-warp per row, coalesced index/value chunk + shuffle broadcast  */
+#define ARROW_VARIANT_TMA      2  /* X rows staged into shared memory with cp.async.bulk + mbarrier     */
+
+int  arrow_b200_abi_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t to run on (e.g. torch's current stream) or NULL: the context then
+ * creates its own non-blocking stream. */
+int  arrow_ctx_create(int device, void *stream, arrow_ctx **out);
+void arrow_ctx_destroy(arrow_ctx *ctx);
+const char *arrow_last_error(const arrow_ctx *ctx);      /* ctx may be NULL: last creation error */
+int  arrow_sync(arrow_ctx *ctx);
+int  arrow_device_info(arrow_ctx *ctx, int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
+int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segment);
+
+/* ---- sparse blocks (replaces _sp2cp, sp2cp.py:6-16: uploaded once, resident) ----------------- */
+/* indptr has n_rows+1 entries of indptr_bytes (4 or 8) each and may start at any base value
+ * (a row slice of a bigger file); indices/data point at the entry indptr[0] refers to.
+ * data == NULL means all ones (missing _data.npy, graphio.py:292-298). */
+int  arrow_csr_upload(arrow_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                      const void *indptr, int indptr_bytes,
+                      const void *indices, int indices_bytes,
+                      const float *data, int *csr_out);
+int  arrow_csr_free(arrow_ctx *ctx, int csr);
+int  arrow_csr_info(arrow_ctx *ctx, int csr, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
+                    int64_t *max_row_nnz, int64_t *n_long_rows);
+/* New CSR sharing indptr/values with `csr`, columns sent through `map` (col' = map[col]; entries
+ * whose image is invalid are skipped by the kernels).  This folds the forward permutation gather
+ * (arrow_dec_mpi.py:526, 544) into the SpMM's X read. */
+int  arrow_csr_remap_columns(arrow_ctx *ctx, int csr, int map, int64_t new_n_cols, int *csr_out);
+
+/* ---- row maps (to_prev / to_next slices, arrow_dec_mpi.py:737-749) ---------------------------- */
+/* int64 host map -> int32 device map; entries < 0 or >= limit (the reference's sentinel
+ * 2*width*n_blocks[0] lands here) become -1 = "not routed". */
+int  arrow_map_upload(arrow_ctx *ctx, const int64_t *map, int64_t n, int64_t limit, int *map_out);
+int  arrow_map_free(arrow_ctx *ctx, int map);
+/* out[r] = outer[inner[r]] (invalid if either step is); chains level maps for the fused path. */
+int  arrow_map_compose(arrow_ctx *ctx, int inner, int outer, int *map_out);
+/* out[q] = r where map[r] == q (injective maps only), size n_out, -1 elsewhere. */
+int  arrow_map_invert(arrow_ctx *ctx, int map, int64_t n_out, int *map_out);
+int  arrow_map_d2h(arrow_ctx *ctx, int map, int32_t *host, int64_t n);
+
+/* ---- dense tiles (X_i / C_i / X_0 / C_0 of arrow_slim_mpi.py:354-394, concatenated) ----------- */
+int  arrow_dense_alloc(arrow_ctx *ctx, int64_t rows, int k, int *buf_out);      /* zero filled */
+int  arrow_dense_free(arrow_ctx *ctx, int buf);
+int  arrow_dense_fill(arrow_ctx *ctx, int buf, float value);
+int  arrow_dense_h2d(arrow_ctx *ctx, int buf, int64_t row0, int64_t rows, const float *host);
+int  arrow_dense_d2h(arrow_ctx *ctx, int buf, int64_t row0, int64_t rows, float *host);
+int  arrow_dense_copy(arrow_ctx *ctx, int dst, int64_t dst_row0, int src, int64_t src_row0, int64_t rows);
+int  arrow_dense_ptr(arrow_ctx *ctx, int buf, void **device_ptr, int64_t *rows, int *k);
+/* Wrap device memory owned by someone else (a torch tensor, an IPC-imported peer tile). */
+int  arrow_dense_wrap(arrow_ctx *ctx, void *device_ptr, int64_t rows, int k, int *buf_out);
+/* pinned host staging */
+int  arrow_host_alloc(size_t bytes, void **ptr);
+int  arrow_host_free(void *ptr);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+/* C[out(r), :] (+)= sum_p A[r, col_p] * X[col_p, :]   for every row r of `csr`
+ *   out(r) = r, or rowmap[r] when rowmap >= 0 (rows with rowmap[r] == -1 are dropped): the backward
+ *   scatter-add of arrow_dec_mpi.py:421-437 folded into the SpMM epilogue.
+ * X must have >= n_cols rows; C must cover every out(r); X and C must not alias. */
+int  arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int flags, int variant);
+
+/* dst[r, :] (+)= src[map[r], :] for r in [0, map length); rows with map[r] == -1 are left alone
+ * (the reference's stale-row behaviour, arrow_dec_mpi.py:544).  Forward exchange with to_prev,
+ * backward exchange (as a gather-add) with to_next. */
+int  arrow_gather_rows(arrow_ctx *ctx, int dst_buf, int src_buf, int map, int flags);
+
+/* Multi-source gather over NVLink peer memory: `map` holds GLOBAL source rows; source s owns global
+ * rows [row_bounds[s], row_bounds[s+1]) and src_bufs[s] is its (wrapped / IPC-imported) tile. */
+int  arrow_gather_rows_multi(arrow_ctx *ctx, int dst_buf, const int *src_bufs,
+                             const int64_t *row_bounds, int n_src, int map, int flags);
+
+/* ---- cross-process peer memory (one process per GPU; NVLink P2P through CUDA IPC) -------------- */
+#define ARROW_IPC_HANDLE_BYTES 64
+int  arrow_ipc_export(arrow_ctx *ctx, int buf, void *handle64);
+int  arrow_ipc_import(arrow_ctx *ctx, const void *handle64, int64_t rows, int k, int *buf_out);
+/* Device-side barrier across `world` ranks over peer-mapped flag words (no host sync, no NCCL):
+ * flags_buf[s] is rank s's flag tile (>= world floats... see DESIGN.md), my slot = rank. */
+int  arrow_peer_barrier(arrow_ctx *ctx, const int *flag_bufs, int rank, int world);
+
+/* ---- timing (CUDA events on the context's stream) ----------------------------------------------- */
+#define ARROW_MAX_TIMERS 32
+int  arrow_timer_start(arrow_ctx *ctx, int slot);
+int  arrow_timer_stop(arrow_ctx *ctx, int slot);
+int  arrow_timer_elapsed_ms(arrow_ctx *ctx, int slot, float *ms);   /* synchronises on the stop event */
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int  arrow_launch_count(arrow_ctx *ctx, int64_t *count);
+
+/* measurement helpers used by bench.py: write `bytes` of scratch (L2 flush) */
+int  arrow_l2_flush(arrow_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARROW_B200_H */

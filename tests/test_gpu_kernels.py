@@ -1,0 +1,215 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Tolerance: fp32, max |err| <= 1e-5 * max |ref| (BASELINE.json: "within 1e-5 relative") and
+np.allclose(rtol=1e-5, atol=1e-5*scale) element-wise -- the reference tests use np.allclose
+defaults (tests/test_arrowmpi.py:304, 329, 396).
+"""
+import numpy as np
+import pytest
+from scipy import sparse
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle
+from arrow_matrix_b200 import _lib, synth
+
+
+def assert_close(got, ref, tol=1e-5):
+    scale = float(np.max(np.abs(ref))) if ref.size else 1.0
+    scale = max(scale, 1e-30)
+    err = float(np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64)))) if ref.size else 0.0
+    assert err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.3e})"
+    assert np.allclose(got, ref, rtol=1e-5, atol=tol * scale)
+
+
+@pytest.fixture(scope="module")
+def ctx(cuda_device):
+    c = _lib.Context(cuda_device)
+    yield c
+    c.close()
+
+
+def ref_spmm64(A, X):
+    return (A.astype(np.float64) @ X.astype(np.float64)).astype(np.float32)
+
+
+@pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_SHFL, _lib.VARIANT_TMA])
+@pytest.mark.parametrize("k", [4, 8, 16, 32, 64, 128, 256, 48])
+def test_spmm_vector_k(ctx, variant, k):
+    rng = np.random.default_rng(42)
+    n = 3000
+    A = synth.generate_sparse_matrix(n, n, 10 * n, np.float32, rng)
+    X = synth.generate_dense_matrix(n, k, np.float32, rng)
+    dA, dX, dC = ctx.csr_from_scipy(A), ctx.dense_from_host(X), ctx.dense_alloc(n, k)
+    ctx.spmm(dA, dX, dC, variant=variant)
+    got = dC.d2h()
+    assert_close(got, oracle.csr_spmm_c(A, X))
+    assert_close(got, A @ X)
+    assert_close(got, ref_spmm64(A, X))
+    # accumulate: C += A X   (arrow_slim_mpi.py:142-144)
+    ctx.spmm(dA, dX, dC, accumulate=True, variant=variant)
+    assert_close(dC.d2h(), 2 * ref_spmm64(A, X))
+    for h in (dA, dX, dC):
+        h.free()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 10, 130, 300])
+def test_spmm_generic_k(ctx, k):
+    # the reference's own tests use k=1 (test_spmm), 4, 10 (test_decomposition), 2 and 5 (test_larger_ranks)
+    rng = np.random.default_rng(7)
+    n = 700
+    A = synth.generate_sparse_matrix(n, n, 6 * n, np.float32, rng)
+    X = synth.generate_dense_matrix(n, k, np.float32, rng)
+    dA, dX, dC = ctx.csr_from_scipy(A), ctx.dense_from_host(X), ctx.dense_alloc(n, k)
+    ctx.spmm(dA, dX, dC)
+    assert_close(dC.d2h(), oracle.csr_spmm_c(A, X))
+    ctx.spmm(dA, dX, dC, accumulate=True)
+    assert_close(dC.d2h(), 2 * ref_spmm64(A, X))
+
+
+@pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_SHFL, _lib.VARIANT_TMA])
+@pytest.mark.parametrize("k", [16, 128, 10])
+def test_spmm_ragged_and_long_rows(ctx, variant, k):
+    """empty rows, 1-entry rows, rows above the long-row threshold (hub rows of the arrow head)."""
+    rng = np.random.default_rng(3)
+    n = 5000
+    lens = rng.integers(0, 12, size=n)
+    lens[::97] = 0
+    lens[5] = 3000          # > threshold 1024: segmented path, 2 segments
+    lens[6] = 4097          # 3 segments
+    lens[4999] = 1025
+    lens[10] = 1024         # exactly at the threshold: regular path
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    cols = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int32)
+    vals = rng.random(cols.size, dtype=np.float32)
+    A = sparse.csr_matrix((vals, cols, indptr), shape=(n, n))
+    X = synth.generate_dense_matrix(n, k, np.float32, rng)
+    dA, dX, dC = ctx.csr_from_scipy(A), ctx.dense_from_host(X), ctx.dense_alloc(n, k)
+    info = dA.info()
+    assert info["n_long_rows"] == 3 and info["max_row_nnz"] == 4097
+    dC.fill(7.0)            # must be overwritten everywhere, also for empty rows
+    ctx.spmm(dA, dX, dC, variant=variant)
+    assert_close(dC.d2h(), ref_spmm64(A, X))
+    ctx.spmm(dA, dX, dC, accumulate=True, variant=variant)
+    assert_close(dC.d2h(), 2 * ref_spmm64(A, X))
+
+
+def test_spmm_int64_inputs_missing_data_and_row_slice(ctx):
+    rng = np.random.default_rng(11)
+    n, k = 2000, 32
+    A = synth.generate_sparse_matrix(n, n, 8 * n, np.float32, rng)
+    X = synth.generate_dense_matrix(n, k, np.float32, rng)
+    # int64 index arrays (Julia converter), no data file -> ones
+    d64 = ctx.csr_upload(n, n, A.indptr.astype(np.int64), A.indices.astype(np.int64), None)
+    dX, dC = ctx.dense_from_host(X), ctx.dense_alloc(n, k)
+    ctx.spmm(d64, dX, dC)
+    ones = sparse.csr_matrix((np.ones_like(A.data), A.indices, A.indptr), shape=A.shape)
+    assert_close(dC.d2h(), ref_spmm64(ones, X))
+    # a row slice with un-rebased indptr (what a sharded loader hands over)
+    r0, r1 = 300, 1700
+    a, b = A.indptr[r0], A.indptr[r1]
+    dS = ctx.csr_upload(r1 - r0, n, A.indptr[r0:r1 + 1], A.indices[a:b], A.data[a:b])
+    dCs = ctx.dense_alloc(r1 - r0, k)
+    ctx.spmm(dS, dX, dCs)
+    assert_close(dCs.d2h(), ref_spmm64(A[r0:r1], X))
+
+
+@pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_SHFL, _lib.VARIANT_TMA])
+@pytest.mark.parametrize("k", [16, 128, 6])
+def test_spmm_fused_permutations(ctx, variant, k):
+    """column remap (forward gather folded in) + rowmap epilogue (backward scatter-add folded in)."""
+    rng = np.random.default_rng(5)
+    n1, n0 = 1500, 4000
+    A = synth.generate_sparse_matrix(n1, n1, 9 * n1, np.float32, rng)
+    A[7, :] = 0
+    A = sparse.csr_matrix(A)
+    A.eliminate_zeros()
+    to_prev = rng.permutation(n0)[:n1].astype(np.int64)
+    to_prev[::50] = 2 * n0                      # sentinel rows (arrow_dec_mpi.py:740-741)
+    X0 = synth.generate_dense_matrix(n0, k, np.float32, rng)
+    C0 = synth.generate_dense_matrix(n0, k, np.float32, rng)
+    valid = to_prev < n0
+    # oracle: X1 = gather (stale rows = 0 here), C1 = A X1, C0[to_prev] += C1
+    X1 = np.zeros((n1, k), np.float32)
+    X1[valid] = X0[to_prev[valid]]
+    C1 = ref_spmm64(A, X1)
+    ref = C0.copy()
+    ref[to_prev[valid]] += C1[valid]
+    m = ctx.map_upload(to_prev, n0)
+    dA = ctx.csr_from_scipy(A)
+    dAf = dA.remap_columns(m, n0)
+    dX0, dC0 = ctx.dense_from_host(X0), ctx.dense_from_host(C0)
+    ctx.spmm(dAf, dX0, dC0, rowmap=m, accumulate=True, variant=variant)
+    assert_close(dC0.d2h(), ref)
+    # without accumulate only routed rows are written
+    dC0.h2d(C0)
+    ctx.spmm(dAf, dX0, dC0, rowmap=m, accumulate=False, variant=variant)
+    ref2 = C0.copy()
+    ref2[to_prev[valid]] = C1[valid]
+    assert_close(dC0.d2h(), ref2)
+
+
+@pytest.mark.parametrize("k", [1, 4, 10, 16, 128])
+def test_gather_rows_forward_backward(ctx, k):
+    rng = np.random.default_rng(9)
+    n0, n1 = 3000, 1200
+    to_prev = rng.permutation(n0)[:n1].astype(np.int64)
+    to_prev[3] = 2 * n0
+    to_prev[77] = 2 * n0
+    X0 = synth.generate_dense_matrix(n0, k, np.float32, rng)
+    stale = synth.generate_dense_matrix(n1, k, np.float32, rng)
+    m = ctx.map_upload(to_prev, n0)
+    d0, d1 = ctx.dense_from_host(X0), ctx.dense_from_host(stale)
+    ctx.gather_rows(d1, d0, m)                          # forward: X1[r] = X0[to_prev[r]], stale rows kept
+    ref = stale.copy()
+    oracle._lib().oracle_gather_rows_f32                # (symbol exists)
+    valid = to_prev < n0
+    ref[valid] = X0[to_prev[valid]]
+    assert np.array_equal(d1.d2h(), ref)                # pure data movement: bit exact
+    # backward as gather-add with the inverted map: C0[to_prev[r]] += C1[r]
+    inv = m.invert(n0)
+    h = inv.to_host()
+    exp_inv = np.full(n0, -1, np.int32)
+    exp_inv[to_prev[valid]] = np.flatnonzero(valid)
+    assert np.array_equal(h, exp_inv)
+    C1 = synth.generate_dense_matrix(n1, k, np.float32, rng)
+    C0 = synth.generate_dense_matrix(n0, k, np.float32, rng)
+    dc1, dc0 = ctx.dense_from_host(C1), ctx.dense_from_host(C0)
+    ctx.gather_rows(dc0, dc1, inv, accumulate=True)
+    refc = C0.copy()
+    refc[to_prev[valid]] += C1[valid]
+    assert np.array_equal(dc0.d2h(), refc)              # one add per element: bit exact
+
+
+def test_gather_rows_multi_source(ctx):
+    rng = np.random.default_rng(13)
+    k = 16
+    bounds = [0, 500, 500, 1300, 2000]                  # one empty source
+    tiles = [synth.generate_dense_matrix(bounds[i + 1] - bounds[i], k, np.float32, rng) for i in range(4)]
+    full = np.concatenate(tiles)
+    m_host = rng.integers(0, 2000, size=900).astype(np.int64)
+    m_host[::10] = -1
+    m = ctx.map_upload(m_host, 2000)
+    srcs = [ctx.dense_from_host(t) if t.shape[0] else ctx.dense_alloc(0, k) for t in tiles]
+    dst = ctx.dense_alloc(900, k)
+    dst.fill(3.0)
+    ctx.gather_rows_multi(dst, srcs, bounds, m)
+    ref = np.full((900, k), 3.0, np.float32)
+    ok = m_host >= 0
+    ref[ok] = full[m_host[ok]]
+    assert np.array_equal(dst.d2h(), ref)
+
+
+def test_errors_are_reported(ctx):
+    with pytest.raises(_lib.ArrowError):
+        ctx.spmm(_lib.Csr(ctx, 999, 1, 1, 0), ctx.dense_alloc(1, 4), ctx.dense_alloc(1, 4))
+    A = ctx.csr_from_scipy(sparse.identity(8, format="csr", dtype=np.float32))
+    x = ctx.dense_alloc(8, 4)
+    with pytest.raises(_lib.ArrowError):
+        ctx.spmm(A, x, x)                                # aliasing
+    with pytest.raises(_lib.ArrowError):
+        ctx.spmm(A, x, ctx.dense_alloc(8, 8))            # k mismatch
+    with pytest.raises(_lib.ArrowError):
+        ctx.spmm(A, ctx.dense_alloc(4, 4), ctx.dense_alloc(8, 4))   # X too short
+    with pytest.raises(_lib.ArrowError):
+        ctx.csr_upload(2, 2, np.array([0, 2, 1]), np.array([0, 1]), None)   # decreasing indptr
