@@ -124,13 +124,16 @@ def arrow_rows(level: Level, width: int, n_blocks: int, block_diagonal: bool, ro
         r = r2
     if have_end < row_end:                       # rows past the end of the file: empty
         out_ptr[max(have_end - row_begin, 0) + 1:] = pos
-    idx = np.concatenate(idx_parts) if len(idx_parts) != 1 else idx_parts[0]
     if not idx_parts:
         idx = np.zeros(0, dtype=np.int32)
+    else:
+        idx = np.concatenate(idx_parts) if len(idx_parts) != 1 else idx_parts[0]
     if data is None:
         dat = None
+    elif not dat_parts:
+        dat = np.zeros(0, dtype=np.float32)
     else:
-        dat = (np.concatenate(dat_parts) if len(dat_parts) != 1 else dat_parts[0]) if dat_parts else np.zeros(0, np.float32)
+        dat = np.concatenate(dat_parts) if len(dat_parts) != 1 else dat_parts[0]
         dat = np.ascontiguousarray(dat, dtype=np.float32)
     return out_ptr, np.ascontiguousarray(idx), dat, dropped
 

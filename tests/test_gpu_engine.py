@@ -99,3 +99,33 @@ def test_arrow_pattern_masking(cuda_device):
     eng.step()
     assert_close(eng.result(), po.step())
     eng.close()
+
+
+# ---- against golden vectors produced by the real reference (tests/golden/make_golden.py) ----------------
+from tests.golden_util import CASES, GoldenCase
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_engine_matches_real_reference_run(cuda_device, name):
+    g = GoldenCase(name)
+    eng = ArrowEngine(g.decomposition, g.width, g.k, block_diagonal=g.block_diagonal, device=cuda_device, mode="exchange")
+    assert eng.n_blocks == g.n_blocks
+    for it in range(g.iterations):
+        if g.X[it] is not None:
+            eng.set_features(g.X[it])
+        eng.step()
+        for j in range(g.L):
+            assert_close(eng.result(j), g.C[it][j])
+    eng.propagate_features()
+    for j in range(g.L):
+        assert_close(eng.result(j), g.final[j])
+    fused_ok = eng.fused_ok
+    eng.close()
+    if fused_ok:
+        eng = ArrowEngine(g.decomposition, g.width, g.k, block_diagonal=g.block_diagonal, device=cuda_device, mode="fused")
+        for it in range(g.iterations):
+            if g.X[it] is not None:
+                eng.set_features(g.X[it])
+            eng.step()
+            assert_close(eng.result(0), g.C[it][0])
+        eng.close()
