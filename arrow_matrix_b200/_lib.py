@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libarrow_b200.so")
 
 ACCUMULATE = 1
-VARIANT_AUTO, VARIANT_DIRECT, VARIANT_SHFL, VARIANT_TMA = -1, 0, 1, 2
+VARIANT_AUTO, VARIANT_DIRECT, VARIANT_SHFL, VARIANT_TMA, VARIANT_TILES = -1, 0, 1, 2, 3
 IPC_HANDLE_BYTES = 64
 
 EXPORTS = [

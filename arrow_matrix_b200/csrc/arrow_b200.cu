@@ -59,6 +59,9 @@ struct Csr {
     int *long_first = nullptr;        // device: first slot of each long row (n_long_rows+1)
     bool owns_long = false;
     int long_threshold = 0;
+    // row tiles for the CSR-streaming kernel: {row_begin, row_end, nnz_begin, nnz_end}
+    int4 *tiles = nullptr;
+    int n_tiles = 0;
     bool live = false;
 };
 
@@ -497,6 +500,136 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) k_spmm_tma(SpmmArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// variant 3 (default): CSR streamed by TMA.  A persistent CTA walks row tiles (<= TILE_ROWS rows,
+// <= TILE_NNZ non-zeros, built at upload).  One elected thread brings the tile's slice of indptr /
+// indices / values into shared memory with three cp.async.bulk copies (UBLKCP) that complete on an
+// mbarrier, one tile ahead of the math (two stages).  Warps then only issue the X gathers: a group of
+// G lanes owns a row, reads (col, val) from shared memory (broadcast) and VPL float4 of the X row.
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_ROWS = 256;
+constexpr int TILE_NNZ = 2048;
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_PTR_WORDS = TILE_ROWS + 8;          // row pointer slice (+ alignment slack)
+constexpr int TILE_NNZ_WORDS = TILE_NNZ + 8;
+constexpr int TILE_STAGE_WORDS = TILE_PTR_WORDS + 2 * TILE_NNZ_WORDS;
+constexpr size_t TILE_SMEM_BYTES = (size_t)2 * TILE_STAGE_WORDS * 4 + 16;
+
+struct TileArgs {
+    SpmmArgs a;
+    const int4 *__restrict__ tiles;
+    int n_tiles;
+    int skip;            // indices may hold -1
+};
+
+template <int G, int VPL, bool ROWMAP, bool ACC>
+__global__ void __launch_bounds__(TILE_THREADS) k_spmm_tiles(TileArgs t) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int *stage_base = reinterpret_cast<int *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)2 * TILE_STAGE_WORDS * 4);
+    const SpmmArgs &a = t.a;
+    constexpr int RPW = 32 / G;
+    constexpr int UNROLL = (VPL >= 4) ? 2 : 4;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int gl = lane % G;
+    const int gi = lane / G;
+    const int k4 = a.k4;
+    const float4 *__restrict__ Xl = reinterpret_cast<const float4 *>(a.X) + gl;
+    float4 *__restrict__ Cl = reinterpret_cast<float4 *>(a.C) + gl;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto prefetch = [&](int tile, int st) {
+        const int4 d = __ldg(t.tiles + tile);
+        const int rb4 = d.x & ~3;
+        const int a0 = d.z & ~3;
+        const uint32_t ptr_bytes = (uint32_t)(((d.y - rb4 + 1) + 3) & ~3) * 4u;
+        const uint32_t nnz_bytes = (uint32_t)(((d.w - a0) + 3) & ~3) * 4u;
+        int *sp = stage_base + (size_t)st * TILE_STAGE_WORDS;
+        mbar_expect_tx(&bars[st], ptr_bytes + 2u * nnz_bytes);
+        bulk_g2s(sp, a.indptr + rb4, ptr_bytes, &bars[st]);
+        if (nnz_bytes) {
+            bulk_g2s(sp + TILE_PTR_WORDS, a.indices + a0, nnz_bytes, &bars[st]);
+            bulk_g2s(sp + TILE_PTR_WORDS + TILE_NNZ_WORDS, a.vals + a0, nnz_bytes, &bars[st]);
+        }
+    };
+
+    uint32_t parity0 = 0u, parity1 = 0u;
+    int tile = blockIdx.x;
+    int st = 0;
+    if (tile < t.n_tiles && threadIdx.x == 0) prefetch(tile, 0);
+    for (; tile < t.n_tiles; tile += gridDim.x, st ^= 1) {
+        const int next = tile + gridDim.x;
+        if (next < t.n_tiles && threadIdx.x == 0) prefetch(next, st ^ 1);
+        const int4 d = __ldg(t.tiles + tile);
+        if (st == 0) { mbar_wait(&bars[0], parity0); parity0 ^= 1u; }
+        else         { mbar_wait(&bars[1], parity1); parity1 ^= 1u; }
+        const int *sp = stage_base + (size_t)st * TILE_STAGE_WORDS;
+        const int *s_ptr = sp + (d.x - (d.x & ~3));
+        const int a0 = d.z & ~3;
+        const int *s_idx = sp + TILE_PTR_WORDS - a0;                    // index with global nnz offsets
+        const float *s_val = reinterpret_cast<const float *>(sp + TILE_PTR_WORDS + TILE_NNZ_WORDS) - a0;
+        const int n_rows_tile = d.y - d.x;
+
+        for (int lr = warp * RPW + gi; lr < n_rows_tile; lr += (TILE_THREADS / 32) * RPW) {
+            const int s = s_ptr[lr];
+            const int e = s_ptr[lr + 1];
+            if (e - s > a.long_threshold) continue;
+            const long long row = (long long)d.x + lr;
+            long long orow = row;
+            if (ROWMAP) {
+                orow = __ldg(a.rowmap + row);
+                if (orow < 0) continue;
+            }
+            float4 acc[VPL];
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) acc[i] = f4_zero();
+            for (int p = s; p < e; p += UNROLL) {
+                int c[UNROLL];
+                float v[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const bool ok = p + u < e;
+                    c[u] = ok ? s_idx[p + u] : -1;
+                    v[u] = ok ? s_val[p + u] : 0.f;
+                }
+                float4 x[UNROLL][VPL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const float4 *xr = Xl + (long long)c[u] * k4;
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i)
+                        x[u][i] = (c[u] >= 0 && gl + i * G < k4) ? __ldg(xr + i * G) : f4_zero();
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
+            }
+            float4 *cr = Cl + orow * k4;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                if (gl + i * G < k4) {
+                    if (ACC) {
+                        float4 old = cr[i * G];
+                        f4_add(acc[i], old);
+                        cr[i * G] = acc[i];
+                    } else {
+                        __stcs(cr + i * G, acc[i]);
+                    }
+                }
+            }
+        }
+        __syncthreads();            // stage `st` may be refilled by the next iteration's prefetch
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic k (not a multiple of 4): warp per row, lanes over columns, scalar accesses.
 // ------------------------------------------------------------------------------------------------
 template <bool ROWMAP, bool ACC>
@@ -774,9 +907,51 @@ int launch_tma(arrow_ctx *ctx, const SpmmArgs &a, bool rowmap, bool acc) {
     return ARROW_OK;
 }
 
+template <int G, int VPL>
+int launch_tiles_gv(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc) {
+#define LAUNCH_TL(KERNEL)                                                                             \
+    do {                                                                                              \
+        auto fn = KERNEL;                                                                             \
+        static bool attr_set = false;                                                                 \
+        static int occ = 0;                                                                           \
+        if (!attr_set) {                                                                              \
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES); \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TILE_THREADS, TILE_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1; \
+            attr_set = true;                                                                          \
+        }                                                                                             \
+        int grid = (int)std::min<long long>((long long)occ * ctx->sm_count, t.n_tiles);               \
+        fn<<<grid, TILE_THREADS, TILE_SMEM_BYTES, ctx->stream>>>(t);                                  \
+    } while (0)
+    if (rowmap && acc) LAUNCH_TL((k_spmm_tiles<G, VPL, true, true>));
+    else if (rowmap) LAUNCH_TL((k_spmm_tiles<G, VPL, true, false>));
+    else if (acc) LAUNCH_TL((k_spmm_tiles<G, VPL, false, true>));
+    else LAUNCH_TL((k_spmm_tiles<G, VPL, false, false>));
+#undef LAUNCH_TL
+    ctx->launches++;
+    return ARROW_OK;
+}
+
+// (lanes per row, float4 per lane) for a k4 = k/4; vpl_req = 0 picks the default
+int launch_tiles(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc, int vpl_req) {
+    const int k4 = t.a.k4;
+    int vpl = vpl_req;
+    if (vpl != 1 && vpl != 2 && vpl != 4) vpl = (k4 >= 16) ? 2 : 1;
+    while (vpl > 1 && k4 < vpl) vpl >>= 1;
+    int lanes = (k4 + vpl - 1) / vpl;                 // lanes needed per row
+    if (lanes > 32) { vpl = (k4 + 31) / 32 <= 2 ? 2 : 4; lanes = (k4 + vpl - 1) / vpl; }
+    int g = 1;
+    while (g < lanes) g <<= 1;
+#define TL(GG, VV) if (g == GG && vpl == VV) return launch_tiles_gv<GG, VV>(ctx, t, rowmap, acc)
+    TL(1, 1); TL(2, 1); TL(4, 1); TL(8, 1); TL(16, 1); TL(32, 1);
+    TL(1, 2); TL(2, 2); TL(4, 2); TL(8, 2); TL(16, 2); TL(32, 2);
+    TL(1, 4); TL(2, 4); TL(4, 4); TL(8, 4); TL(16, 4);
+#undef TL
+    return fail(ctx, ARROW_ERR_UNSUPPORTED, "no tile kernel for k4=%d vpl=%d", k4, vpl);
+}
+
 int pick_variant(int k) {
     (void)k;
-    return ARROW_VARIANT_SHFL;
+    return 3;
 }
 
 }  // namespace
@@ -848,6 +1023,7 @@ void arrow_ctx_destroy(arrow_ctx *ctx) {
                 cudaFree(c.long_tasks);
                 cudaFree(c.long_rows);
                 cudaFree(c.long_first);
+                cudaFree(c.tiles);
             }
         }
     for (auto &m : ctx->maps)
@@ -887,7 +1063,8 @@ int arrow_device_info(arrow_ctx *ctx, int *sm_count, int64_t *free_bytes, int64_
 
 int arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segment) {
     CHECK_CTX(ctx);
-    if (long_row_threshold < 1 || long_row_segment < 32) return fail(ctx, ARROW_ERR_ARG, "bad tuning values");
+    if (long_row_threshold < 1 || long_row_segment < 32 || long_row_threshold > TILE_NNZ - 8)
+        return fail(ctx, ARROW_ERR_ARG, "bad tuning values (threshold must be in [1, %d])", TILE_NNZ - 8);
     ctx->long_threshold = long_row_threshold;
     ctx->long_segment = long_row_segment;
     return ARROW_OK;
@@ -911,15 +1088,39 @@ static int build_long_rows(arrow_ctx *ctx, Csr &c, const std::vector<int> &h_ind
         }
     }
     first.push_back((int)tasks.size());
+    // row tiles for k_spmm_tiles: contiguous rows, <= TILE_ROWS rows and <= TILE_NNZ entries, cut around long rows
+    {
+        std::vector<int4> tiles;
+        int64_t r = 0;
+        while (r < c.n_rows) {
+            const int len0 = h_indptr[r + 1] - h_indptr[r];
+            if (len0 > thr) { ++r; continue; }                     // long rows are not tiled
+            int64_t e = r;
+            while (e < c.n_rows && e - r < TILE_ROWS) {
+                const int len = h_indptr[e + 1] - h_indptr[e];
+                if (len > thr) break;
+                if (h_indptr[e + 1] - h_indptr[r] > TILE_NNZ - 4 && e > r) break;
+                ++e;
+            }
+            if (e == r) ++e;                                       // a single row always fits: thr <= TILE_NNZ - 8
+            tiles.push_back(make_int4((int)r, (int)e, h_indptr[r], h_indptr[e]));
+            r = e;
+        }
+        c.n_tiles = (int)tiles.size();
+        if (!tiles.empty()) {
+            CUDA_TRY(ctx, cudaMalloc(&c.tiles, tiles.size() * sizeof(int4)));
+            CUDA_TRY(ctx, cudaMemcpy(c.tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+        }
+    }
     c.max_row_nnz = mx;
     c.long_threshold = thr;
     c.n_long_rows = (int)rows.size();
     c.n_long_tasks = (int)tasks.size();
+    c.owns_long = true;
     if (!rows.empty()) {
         CUDA_TRY(ctx, cudaMalloc(&c.long_tasks, tasks.size() * sizeof(LongTask)));
         CUDA_TRY(ctx, cudaMalloc(&c.long_rows, rows.size() * sizeof(int)));
         CUDA_TRY(ctx, cudaMalloc(&c.long_first, first.size() * sizeof(int)));
-        c.owns_long = true;
         CUDA_TRY(ctx, cudaMemcpy(c.long_tasks, tasks.data(), tasks.size() * sizeof(LongTask), cudaMemcpyHostToDevice));
         CUDA_TRY(ctx, cudaMemcpy(c.long_rows, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice));
         CUDA_TRY(ctx, cudaMemcpy(c.long_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -966,14 +1167,17 @@ int arrow_csr_upload(arrow_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz
     c.n_rows = n_rows;
     c.n_cols = n_cols;
     c.nnz = nnz;
-    CUDA_TRY(ctx, cudaMalloc(&c.indptr, ((size_t)n_rows + 1) * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc(&c.indptr, ((size_t)n_rows + 1 + 8) * sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(c.indptr, 0, ((size_t)n_rows + 1 + 8) * sizeof(int), ctx->stream));
     c.owns_indptr = true;
     CUDA_TRY(ctx, cudaMemcpyAsync(c.indptr, h_indptr.data(), ((size_t)n_rows + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    const size_t nz = (size_t)std::max<int64_t>(nnz, 1);
+    const size_t nz = (size_t)nnz + 8;                       // slack: bulk copies round up to 16 bytes
     CUDA_TRY(ctx, cudaMalloc(&c.indices, nz * sizeof(int)));
     c.owns_indices = true;
     CUDA_TRY(ctx, cudaMalloc(&c.vals, nz * sizeof(float)));
     c.owns_vals = true;
+    CUDA_TRY(ctx, cudaMemsetAsync(c.indices, 0, nz * sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(c.vals, 0, nz * sizeof(float), ctx->stream));
     if (nnz > 0) {
         if (indices_bytes == 4) {
             CUDA_TRY(ctx, cudaMemcpyAsync(c.indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1023,6 +1227,7 @@ int arrow_csr_free(arrow_ctx *ctx, int csr) {
         cudaFree(c->long_tasks);
         cudaFree(c->long_rows);
         cudaFree(c->long_first);
+        cudaFree(c->tiles);
     }
     *c = Csr();
     return ARROW_OK;
@@ -1054,7 +1259,8 @@ int arrow_csr_remap_columns(arrow_ctx *ctx, int csr, int map, int64_t new_n_cols
     d.indices = nullptr;
     d.n_cols = new_n_cols;
     d.may_skip = true;
-    CUDA_TRY(ctx, cudaMalloc(&d.indices, (size_t)std::max<int64_t>(c->nnz, 1) * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc(&d.indices, ((size_t)c->nnz + 8) * sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(d.indices, 0, ((size_t)c->nnz + 8) * sizeof(int), ctx->stream));
     if (c->nnz > 0) {
         k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->indices, m->p, m->n, d.indices, c->nnz);
         ctx->launches++;
@@ -1317,7 +1523,9 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
     a.k4 = k / 4;
     a.long_threshold = A->long_threshold;
     if (variant == ARROW_VARIANT_AUTO) variant = pick_variant(k);
-    if (variant < 0 || variant > 2) return fail(ctx, ARROW_ERR_ARG, "unknown variant %d", variant);
+    const int vpl_req = (variant >> 4) & 0xF;          // optional float4-per-lane override (tile kernel)
+    variant &= 0xF;
+    if (variant < 0 || variant > 3) return fail(ctx, ARROW_ERR_ARG, "unknown variant %d", variant);
 
     const bool vec_ok = (k % 4 == 0) && k <= 256;
     if (!vec_ok) {
@@ -1334,7 +1542,17 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
         else LAUNCH_G((k_spmm_generic<false, false>));
 #undef LAUNCH_G
         ctx->launches++;
-    } else if (variant == ARROW_VARIANT_TMA && k >= 32) {
+    } else if (variant == 3) {
+        if (A->n_tiles > 0) {
+            TileArgs t;
+            t.a = a;
+            t.tiles = A->tiles;
+            t.n_tiles = A->n_tiles;
+            t.skip = A->may_skip ? 1 : 0;
+            int rc = launch_tiles(ctx, t, rm != nullptr, acc, vpl_req);
+            if (rc != ARROW_OK) return rc;
+        }
+    } else if (variant == ARROW_VARIANT_TMA && k >= 32 && k <= 128) {
         if (a.k4 <= 32) launch_tma<1>(ctx, a, rm != nullptr, acc);
         else launch_tma<2>(ctx, a, rm != nullptr, acc);
     } else {

@@ -48,6 +48,9 @@ typedef struct arrow_ctx arrow_ctx;
 #define ARROW_VARIANT_DIRECT   0  /* sub-warp per row, broadcast index loads, float4 X gathers          */
 #define ARROW_VARIANT_SHFL     1  /* sub-warp per row, coalesced index/value chunk + shuffle broadcast  */
 #define ARROW_VARIANT_TMA      2  /* X rows staged into shared memory with cp.async.bulk + mbarrier     */
+#define ARROW_VARIANT_TILES    3  /* default: CSR row tiles streamed by cp.async.bulk (TMA) + mbarrier,
+                                     two stages; warps only issue X gathers.  Bits 4..7 of `variant`
+                                     optionally force the float4-per-lane count (1, 2 or 4).           */
 
 int  arrow_b200_abi_version(void);
 

@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=100)
     ap.add_argument("--width", type=int, default=10000)
     ap.add_argument("--ks", type=str, default="16,32,64,128,256")
-    ap.add_argument("--variants", type=str, default="0,1,2")
+    ap.add_argument("--variants", type=str, default="0,1,3,19,35,67")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--uniform", action="store_true", help="utils.generate_sparse_matrix recipe instead of arrow shaped")
     ap.add_argument("--peak", type=float, default=0.0)
@@ -61,7 +61,7 @@ def main():
         alg_bytes = A.nnz * 8 + (n + 1) * 4 + 2.0 * n * k * 4
         flops = 2.0 * A.nnz * k
         for v in [int(x) for x in args.variants.split(",")]:
-            if v == 2 and k < 32:
+            if v == 2 and (k < 32 or k > 128):
                 continue
             for _ in range(3):
                 ctx.spmm(dA, dX, dC, variant=v)

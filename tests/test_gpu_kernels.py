@@ -14,6 +14,11 @@ from oracle import oracle
 from arrow_matrix_b200 import _lib, synth
 
 
+# kernel kinds; for the CSR-streaming tile kernel also force 1 / 2 / 4 float4 per lane (bits 4..7)
+ALL_VARIANTS = [_lib.VARIANT_DIRECT, _lib.VARIANT_SHFL, _lib.VARIANT_TMA, _lib.VARIANT_TILES,
+                _lib.VARIANT_TILES | (1 << 4), _lib.VARIANT_TILES | (2 << 4), _lib.VARIANT_TILES | (4 << 4)]
+
+
 def assert_close(got, ref, tol=1e-5):
     scale = float(np.max(np.abs(ref))) if ref.size else 1.0
     scale = max(scale, 1e-30)
@@ -33,7 +38,7 @@ def ref_spmm64(A, X):
     return (A.astype(np.float64) @ X.astype(np.float64)).astype(np.float32)
 
 
-@pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_SHFL, _lib.VARIANT_TMA])
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
 @pytest.mark.parametrize("k", [4, 8, 16, 32, 64, 128, 256, 48])
 def test_spmm_vector_k(ctx, variant, k):
     rng = np.random.default_rng(42)
@@ -67,7 +72,7 @@ def test_spmm_generic_k(ctx, k):
     assert_close(dC.d2h(), 2 * ref_spmm64(A, X))
 
 
-@pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_SHFL, _lib.VARIANT_TMA])
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
 @pytest.mark.parametrize("k", [16, 128, 10])
 def test_spmm_ragged_and_long_rows(ctx, variant, k):
     """empty rows, 1-entry rows, rows above the long-row threshold (hub rows of the arrow head)."""
@@ -114,7 +119,7 @@ def test_spmm_int64_inputs_missing_data_and_row_slice(ctx):
     assert_close(dCs.d2h(), ref_spmm64(A[r0:r1], X))
 
 
-@pytest.mark.parametrize("variant", [_lib.VARIANT_DIRECT, _lib.VARIANT_SHFL, _lib.VARIANT_TMA])
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
 @pytest.mark.parametrize("k", [16, 128, 6])
 def test_spmm_fused_permutations(ctx, variant, k):
     """column remap (forward gather folded in) + rowmap epilogue (backward scatter-add folded in)."""
