@@ -1,0 +1,103 @@
+"""CPU tests of the host-side surface: C-ABI exports, loud failure without a GPU, loader, routing tables."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from arrow_matrix_b200 import _lib, graphio, synth
+from arrow_matrix_b200.arrow_dec_mpi import ArrowDecompositionMPI
+from arrow_matrix_b200.arrow_matrix import ArrowMatrix
+from arrow_matrix_b200.arrow_slim_mpi import ArrowSlimMPI
+from tests.golden_util import GOLDEN_DIR
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "arrow_b200.h")).read()
+    declared = set(re.findall(r"\b(arrow_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = _lib.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libarrow_b200.so does not export {name}"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.arrow_b200_abi_version() == 1
+
+
+@pytest.mark.skipif(_cuda(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu():
+    with pytest.raises(_lib.ArrowError) as e:
+        _lib.Context(0)
+    assert "no CPU fallback" in str(e.value)
+    from arrow_matrix_b200.engine import ArrowEngine
+    dec = synth.synth_decomposition(2, 8, levels=1)
+    with pytest.raises(_lib.ArrowError):
+        ArrowEngine(dec, 8, 4)
+
+
+def test_device_cpu_is_refused():
+    from arrow_matrix_b200.comm import SelfComm
+    with pytest.raises(NotImplementedError):
+        ArrowDecompositionMPI.initialize(SelfComm(), np.array([2, 1]), None, None, 8, 4, device='cpu')
+    with pytest.raises(NotImplementedError):
+        ArrowSlimMPI(SelfComm()).spmm(device='cpu')
+
+
+def test_surface_has_reference_methods():
+    for name in ["result_tile", "feature_tile", "spmm", "set_features", "load_sparse_matrix_from_blocks",
+                 "is_column_rank", "zero_rhs", "allgather_result", "set_features_slice_from_features"]:
+        assert name in ArrowMatrix.__abstractmethods__
+        assert callable(getattr(ArrowSlimMPI, name))
+    for name in ["load_decomposition_new", "initialize", "step", "_propagate_features", "_aggregate",
+                 "_all_to_all_tables", "number_of_blocks", "load_data_from_blocks"]:
+        assert callable(getattr(ArrowDecompositionMPI, name))
+
+
+def test_all_to_all_tables_product_version_against_reference_outputs():
+    z = np.load(os.path.join(GOLDEN_DIR, "all_to_all_tables.npz"))
+    for i in range(int(z["n"])):
+        head = z[f"in_{i}"]
+        rpr, cols, total, off = (int(x) for x in head[:4])
+        c, d, sp, rp = ArrowDecompositionMPI._all_to_all_tables(head[4:], rpr, cols, total, off)
+        assert np.array_equal(c, z[f"counts_{i}"]) and np.array_equal(d, z[f"displs_{i}"])
+        assert np.array_equal(sp, z[f"send_{i}"]) and np.array_equal(rp, z[f"recv_{i}"])
+    # the reference's own assertions (tests/test_arrowmpi.py:24-47)
+    ranks, prev_ranks, rpr, cols = 2, 6, 4, 6
+    perm = np.asarray(list(reversed(range(ranks * rpr))))
+    for i in range(ranks):
+        sl = perm[i * rpr:(i + 1) * rpr]
+        counts, displs, p, out_p = ArrowDecompositionMPI._all_to_all_tables(sl, rpr, cols, prev_ranks + ranks, prev_ranks)
+        assert counts[ranks + prev_ranks - i - 1] == rpr * cols and sum(counts) == rpr * cols
+        assert displs[ranks + prev_ranks - i - 1] == 0
+
+
+def test_load_decomposition_new_surface(tmp_path):
+    from arrow_matrix_b200.comm import SelfComm
+    dec = synth.synth_decomposition(4, 8, levels=2, perm_kind="random", seed=9)
+    base = str(tmp_path / "g")
+    graphio.save_decomposition_new(dec, base, 8, True)
+    blocks, n_blocks, to_prev, to_next = ArrowDecompositionMPI.load_decomposition_new(SelfComm(), base, 8, True, slim=True)
+    assert list(n_blocks) == [4, 2] and n_blocks.dtype == np.int32
+    assert to_prev[0] is None and to_next[1] is None
+    assert np.array_equal(to_prev[1], dec[1][1])            # level 0 is the identity
+    assert blocks.width == 8 and len(blocks.decomposition) == 2
+    # missing files: same "nothing found" signalling as the reference (None + empty n_blocks)
+    b2, nb2, _, _ = ArrowDecompositionMPI.load_decomposition_new(SelfComm(), str(tmp_path / "nope"), 8, True)
+    assert b2 is None and nb2.size == 0
+
+
+def test_cli_flags_match_reference():
+    from arrow_matrix_b200 import cli
+    import argparse
+    with pytest.raises(SystemExit):
+        cli.main(["--help"])
+    assert cli.str2bool("yes") and not cli.str2bool("0")
