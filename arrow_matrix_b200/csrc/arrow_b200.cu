@@ -91,7 +91,7 @@ struct arrow_ctx {
     std::vector<IdxMap> maps;
     Timer timers[ARROW_MAX_TIMERS];
     int64_t launches = 0;
-    int long_threshold = 1024;
+    int long_threshold = 512;
     int long_segment = 2048;
     float *long_scratch = nullptr;    // [slots][k] partial sums of long-row segments
     size_t long_scratch_bytes = 0;
@@ -185,10 +185,13 @@ struct SpmmArgs {
 // variant 0: a group of G lanes owns one row; every lane of the group reads the same index/value
 // (hardware broadcast) and its own float4 slice of the X row.  UNROLL independent X gathers in flight.
 // ------------------------------------------------------------------------------------------------
+// __launch_bounds__(256, 4): without the min-blocks bound ptxas aims at full occupancy (<= 40 registers)
+// and serialises every gather behind the FFMAs of the previous one; with it all UNROLL gathers of a
+// batch are issued back to back (checked in SASS), which is what hides the L2 / HBM latency.
 template <int G, int VPL, bool ROWMAP, bool ACC>
-__global__ void __launch_bounds__(256) k_spmm_direct(SpmmArgs a) {
+__global__ void __launch_bounds__(256, 4) k_spmm_direct(SpmmArgs a) {
     constexpr int RPW = 32 / G;
-    constexpr int UNROLL = (VPL == 1) ? 4 : 2;
+    constexpr int UNROLL = (VPL == 1) ? 8 : 4;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;                      // lane inside the group
     const int gi = lane / G;                      // group inside the warp
@@ -255,9 +258,10 @@ __global__ void __launch_bounds__(256) k_spmm_direct(SpmmArgs a) {
 // each and broadcasts them with width-G shuffles; the X gathers are issued UNROLL at a time.
 // ------------------------------------------------------------------------------------------------
 template <int G, int VPL, bool ROWMAP, bool ACC>
-__global__ void __launch_bounds__(256) k_spmm_shfl(SpmmArgs a) {
+__global__ void __launch_bounds__(256, 4) k_spmm_shfl(SpmmArgs a) {
     constexpr int RPW = 32 / G;
-    constexpr int UNROLL = (G >= 4) ? ((VPL == 1) ? 4 : 2) : G;
+    constexpr int UWANT = (VPL == 1) ? 8 : 4;
+    constexpr int UNROLL = (G >= UWANT) ? UWANT : G;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const int gi = lane / G;
@@ -506,8 +510,8 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) k_spmm_tma(SpmmArgs a) {
 // mbarrier, one tile ahead of the math (two stages).  Warps then only issue the X gathers: a group of
 // G lanes owns a row, reads (col, val) from shared memory (broadcast) and VPL float4 of the X row.
 // ------------------------------------------------------------------------------------------------
-constexpr int TILE_ROWS = 256;
-constexpr int TILE_NNZ = 2048;
+constexpr int TILE_ROWS = 64;       // small tiles keep the rows in flight (grid x TILE_ROWS) inside ~4 blocks => L2 hits
+constexpr int TILE_NNZ = 1024;
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_PTR_WORDS = TILE_ROWS + 8;          // row pointer slice (+ alignment slack)
 constexpr int TILE_NNZ_WORDS = TILE_NNZ + 8;
@@ -522,13 +526,13 @@ struct TileArgs {
 };
 
 template <int G, int VPL, bool ROWMAP, bool ACC>
-__global__ void __launch_bounds__(TILE_THREADS) k_spmm_tiles(TileArgs t) {
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int *stage_base = reinterpret_cast<int *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)2 * TILE_STAGE_WORDS * 4);
     const SpmmArgs &a = t.a;
     constexpr int RPW = 32 / G;
-    constexpr int UNROLL = (VPL >= 4) ? 2 : 4;
+    constexpr int UNROLL = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int gl = lane % G;

@@ -22,13 +22,13 @@
 /* Y (n_row x k, row-major) += A (CSR) * X (n_col x k, row-major). */
 void oracle_csr_matvecs_f32_i32(int64_t n_row, int64_t k, const int32_t *indptr,
                                 const int32_t *indices, const float *data,
-                                const float *x, float *y)
+                                const float *restrict x, float *restrict y)
 {
     for (int64_t i = 0; i < n_row; ++i) {
-        float *yi = y + (size_t)i * (size_t)k;
+        float *restrict yi = y + (size_t)i * (size_t)k;
         for (int32_t jj = indptr[i]; jj < indptr[i + 1]; ++jj) {
             const float a = data[jj];
-            const float *xj = x + (size_t)indices[jj] * (size_t)k;
+            const float *restrict xj = x + (size_t)indices[jj] * (size_t)k;
             for (int64_t c = 0; c < k; ++c)
                 yi[c] += a * xj[c];
         }
@@ -37,13 +37,13 @@ void oracle_csr_matvecs_f32_i32(int64_t n_row, int64_t k, const int32_t *indptr,
 
 void oracle_csr_matvecs_f32_i64(int64_t n_row, int64_t k, const int64_t *indptr,
                                 const int64_t *indices, const float *data,
-                                const float *x, float *y)
+                                const float *restrict x, float *restrict y)
 {
     for (int64_t i = 0; i < n_row; ++i) {
-        float *yi = y + (size_t)i * (size_t)k;
+        float *restrict yi = y + (size_t)i * (size_t)k;
         for (int64_t jj = indptr[i]; jj < indptr[i + 1]; ++jj) {
             const float a = data[jj];
-            const float *xj = x + (size_t)indices[jj] * (size_t)k;
+            const float *restrict xj = x + (size_t)indices[jj] * (size_t)k;
             for (int64_t c = 0; c < k; ++c)
                 yi[c] += a * xj[c];
         }
@@ -54,13 +54,13 @@ void oracle_csr_matvecs_f32_i64(int64_t n_row, int64_t k, const int64_t *indptr,
  * the reference splits block-rows over MPI ranks. */
 void oracle_csr_matvecs_f32_i32_rows(int64_t row_begin, int64_t row_end, int64_t k,
                                      const int32_t *indptr, const int32_t *indices,
-                                     const float *data, const float *x, float *y)
+                                     const float *data, const float *restrict x, float *restrict y)
 {
     for (int64_t i = row_begin; i < row_end; ++i) {
-        float *yi = y + (size_t)i * (size_t)k;
+        float *restrict yi = y + (size_t)i * (size_t)k;
         for (int32_t jj = indptr[i]; jj < indptr[i + 1]; ++jj) {
             const float a = data[jj];
-            const float *xj = x + (size_t)indices[jj] * (size_t)k;
+            const float *restrict xj = x + (size_t)indices[jj] * (size_t)k;
             for (int64_t c = 0; c < k; ++c)
                 yi[c] += a * xj[c];
         }
@@ -90,4 +90,34 @@ void oracle_scatter_add_rows_f32(int64_t n_src, int64_t k, const int64_t *map, i
         if (d < 0 || d >= dst_rows) continue;
         for (int64_t c = 0; c < k; ++c) dst[(size_t)d * k + c] += src[(size_t)r * k + c];
     }
+}
+
+/* Row-range forms of the two exchanges so host threads can split them like MPI ranks split tiles. */
+void oracle_gather_rows_f32_range(int64_t r_begin, int64_t r_end, int64_t k, const int64_t *map,
+                                  int64_t src_rows, const float *src, float *dst)
+{
+    for (int64_t r = r_begin; r < r_end; ++r) {
+        int64_t s = map[r];
+        if (s < 0 || s >= src_rows) continue;
+        const float *sp = src + (size_t)s * k;
+        float *dp = dst + (size_t)r * k;
+        for (int64_t c = 0; c < k; ++c) dp[c] = sp[c];
+    }
+}
+
+void oracle_scatter_add_rows_f32_range(int64_t r_begin, int64_t r_end, int64_t k, const int64_t *map,
+                                       int64_t dst_rows, const float *src, float *dst)
+{
+    for (int64_t r = r_begin; r < r_end; ++r) {
+        int64_t d = map[r];
+        if (d < 0 || d >= dst_rows) continue;
+        const float *sp = src + (size_t)r * k;
+        float *dp = dst + (size_t)d * k;
+        for (int64_t c = 0; c < k; ++c) dp[c] += sp[c];
+    }
+}
+
+void oracle_zero_rows_f32(int64_t r_begin, int64_t r_end, int64_t k, float *dst)
+{
+    for (size_t i = (size_t)r_begin * k; i < (size_t)r_end * k; ++i) dst[i] = 0.0f;
 }

@@ -80,10 +80,10 @@ def test_spmm_ragged_and_long_rows(ctx, variant, k):
     n = 5000
     lens = rng.integers(0, 12, size=n)
     lens[::97] = 0
-    lens[5] = 3000          # > threshold 1024: segmented path, 2 segments
+    lens[5] = 3000          # > threshold 512: segmented path, 2 segments
     lens[6] = 4097          # 3 segments
-    lens[4999] = 1025
-    lens[10] = 1024         # exactly at the threshold: regular path
+    lens[4999] = 513
+    lens[10] = 512          # exactly at the threshold: regular path
     indptr = np.concatenate([[0], np.cumsum(lens)])
     cols = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int32)
     vals = rng.random(cols.size, dtype=np.float32)
@@ -217,4 +217,4 @@ def test_errors_are_reported(ctx):
     with pytest.raises(_lib.ArrowError):
         ctx.spmm(A, ctx.dense_alloc(4, 4), ctx.dense_alloc(8, 4))   # X too short
     with pytest.raises(_lib.ArrowError):
-        ctx.csr_upload(2, 2, np.array([0, 2, 1]), np.array([0, 1]), None)   # decreasing indptr
+        ctx.csr_upload(2, 2, np.array([0, 2, 1]), np.array([0]), None)      # decreasing indptr
