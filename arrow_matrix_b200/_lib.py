@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libarrow_b200.so")
 
 ACCUMULATE = 1
 VARIANT_AUTO, VARIANT_DIRECT, VARIANT_SHFL, VARIANT_TMA, VARIANT_TILES = -1, 0, 1, 2, 3
-IPC_HANDLE_BYTES = 64
+IPC_HANDLE_BYTES = 80
 
 EXPORTS = [
     "arrow_b200_abi_version", "arrow_ctx_create", "arrow_ctx_destroy", "arrow_last_error", "arrow_sync",

@@ -45,8 +45,9 @@ class ArrowSlimMPI(ArrowMatrix):
         eng.ctx.spmm(st.csr, st.bufs[st.xi], st.bufs[out], variant=eng.variant)
         st.ci = out
 
-    def result_tile(self) -> np.ndarray:
-        return self._engine.result(self._level)
+    def result_tile(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host copy of the result rows; pass a (pinned) ``out`` array to avoid an allocation per call."""
+        return self._engine.result(self._level, out)
 
     @property
     def C_i(self) -> np.ndarray:

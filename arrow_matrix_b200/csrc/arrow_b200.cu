@@ -13,6 +13,7 @@
 #include "../../include/arrow_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -33,6 +34,7 @@ struct DenseBuf {
     int k = 0;
     bool owned = false;
     bool ipc = false;
+    void *ipc_base = nullptr;
     bool live = false;
 };
 
@@ -939,7 +941,8 @@ int launch_tiles_gv(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc) {
 int launch_tiles(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc, int vpl_req) {
     const int k4 = t.a.k4;
     int vpl = vpl_req;
-    if (vpl != 1 && vpl != 2 && vpl != 4) vpl = (k4 >= 16) ? 2 : 1;
+    // measured on B200 (profiles/r01_kernel_sweep.md): ~8 lanes per row is the sweet spot
+    if (vpl != 1 && vpl != 2 && vpl != 4) vpl = (k4 >= 32) ? 4 : (k4 >= 8 ? 2 : 1);
     while (vpl > 1 && k4 < vpl) vpl >>= 1;
     int lanes = (k4 + vpl - 1) / vpl;                 // lanes needed per row
     if (lanes > 32) { vpl = (k4 + 31) / 32 <= 2 ? 2 : 4; lanes = (k4 + vpl - 1) / vpl; }
@@ -1016,7 +1019,7 @@ void arrow_ctx_destroy(arrow_ctx *ctx) {
     for (auto &d : ctx->dense)
         if (d.live) {
             if (d.owned) cudaFree(d.p);
-            else if (d.ipc) cudaIpcCloseMemHandle(d.p);
+            else if (d.ipc) cudaIpcCloseMemHandle(d.ipc_base);
         }
     for (auto &c : ctx->csrs)
         if (c.live) {
@@ -1398,7 +1401,7 @@ int arrow_dense_free(arrow_ctx *ctx, int buf) {
     if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (d->owned) cudaFree(d->p);
-    else if (d->ipc) cudaIpcCloseMemHandle(d->p);
+    else if (d->ipc) cudaIpcCloseMemHandle(d->ipc_base);
     *d = DenseBuf();
     return ARROW_OK;
 }
@@ -1673,26 +1676,52 @@ int arrow_gather_rows_multi(arrow_ctx *ctx, int dst_buf, const int *src_bufs, co
 }
 
 // ---- IPC / peer barrier -------------------------------------------------------------------------
-int arrow_ipc_export(arrow_ctx *ctx, int buf, void *handle64) {
+// cudaIpcGetMemHandle names the whole underlying allocation; a pointer that was sub-allocated inside a larger
+// driver block must be re-based on the importing side.  The base comes from the driver (cuMemGetAddressRange),
+// resolved at run time so the library does not link libcuda.
+static long long ipc_base_offset(void *ptr) {
+    typedef int (*range_fn)(unsigned long long *, size_t *, unsigned long long);
+    static range_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = dlopen("libcuda.so.1", RTLD_LAZY | RTLD_GLOBAL);
+        if (h) fn = (range_fn)dlsym(h, "cuMemGetAddressRange_v2");
+    }
+    if (!fn) return 0;
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)ptr) != 0) return 0;
+    return (long long)((unsigned long long)ptr - base);
+}
+
+int arrow_ipc_export(arrow_ctx *ctx, int buf, void *handle) {
     CHECK_CTX(ctx);
     DenseBuf *d = get_dense(ctx, buf);
     if (!d || !d->owned) return fail(ctx, ARROW_ERR_HANDLE, "ipc export needs a tile this context allocated (handle %d)", buf);
-    static_assert(sizeof(cudaIpcMemHandle_t) == ARROW_IPC_HANDLE_BYTES, "ipc handle size");
+    if (!handle) return fail(ctx, ARROW_ERR_ARG, "handle is null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
     cudaIpcMemHandle_t h;
     CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, d->p));
-    memcpy(handle64, &h, sizeof h);
+    memset(handle, 0, ARROW_IPC_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    const long long off = ipc_base_offset(d->p);
+    memcpy((char *)handle + 64, &off, sizeof off);
     return ARROW_OK;
 }
 
-int arrow_ipc_import(arrow_ctx *ctx, const void *handle64, int64_t rows, int k, int *buf_out) {
+int arrow_ipc_import(arrow_ctx *ctx, const void *handle, int64_t rows, int k, int *buf_out) {
     CHECK_CTX(ctx);
-    if (!handle64 || !buf_out || rows < 0 || k < 1) return fail(ctx, ARROW_ERR_ARG, "bad ipc import arguments");
+    if (!handle || !buf_out || rows < 0 || k < 1) return fail(ctx, ARROW_ERR_ARG, "bad ipc import arguments");
     cudaIpcMemHandle_t h;
-    memcpy(&h, handle64, sizeof h);
+    memcpy(&h, handle, sizeof h);
+    long long off = 0;
+    memcpy(&off, (const char *)handle + 64, sizeof off);
     void *p = nullptr;
     CUDA_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     DenseBuf d;
-    d.p = (float *)p;
+    d.p = (float *)((char *)p + off);
+    d.ipc_base = p;
     d.rows = rows;
     d.k = k;
     d.ipc = true;

@@ -139,5 +139,9 @@ def arrow_rows(level: Level, width: int, n_blocks: int, block_diagonal: bool, ro
 
 
 def block_partition(n_blocks: int, parts: int) -> np.ndarray:
-    """Contiguous, as-even-as-possible split of ``n_blocks`` block-rows over ``parts`` GPUs (bounds array)."""
-    return (np.arange(parts + 1, dtype=np.int64) * n_blocks) // parts
+    """Contiguous, as-even-as-possible split of ``n_blocks`` block-rows over ``parts`` GPUs (bounds array).
+
+    Ceil-based so the low ranks fill first: block-row 0 (the arrow head, which the sharded engine keeps on
+    rank 0) always belongs to rank 0, and with fewer blocks than GPUs the trailing ranks own nothing."""
+    g = np.arange(parts + 1, dtype=np.int64)
+    return (g * n_blocks + parts - 1) // parts

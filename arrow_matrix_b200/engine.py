@@ -140,6 +140,14 @@ class ArrowEngine:
         if sync:
             self.ctx.sync()
 
+    def rewind_features(self):
+        """Point level 0 back at the tile the last ``set_features`` filled (no copy), so the next ``step()``
+        multiplies the same features again instead of chaining -- the benchmark's "fresh X every iteration"
+        (``arrow_bench.py:113-116``) without a host round trip.  ``step()`` never writes that tile."""
+        st = self.levels[0]
+        if st.xi == st.ci:
+            st.xi = 1 - st.ci
+
     def features_buffer(self) -> _lib.Dense:
         st = self.levels[0]
         return st.bufs[st.xi]
@@ -212,6 +220,23 @@ class ArrowEngine:
                 m = int(np.count_nonzero(st.to_prev < self.levels[j - 1].rows))
                 total += 5.0 * m * self.k * 4
         return total
+
+    def time_level_spmm(self, j: int, iters: int, warmup: int = 3) -> float:
+        """Average duration (ms) of level ``j``'s plain arrow SpMM launch, CUDA events on the engine's stream."""
+        st = self.levels[j]
+        src = self.levels[0].bufs[self.levels[0].xi] if (self.mode == "fused" and j > 0) else st.bufs[st.xi]
+        if j > 0 and self.mode == "fused":
+            raise ValueError("levels > 0 have no standalone launch in fused mode")
+        scratch = self.ctx.dense_alloc(st.rows, self.k)
+        for _ in range(warmup):
+            self.ctx.spmm(st.csr, src, scratch, variant=self.variant)
+        self.ctx.timer_start(5)
+        for _ in range(iters):
+            self.ctx.spmm(st.csr, src, scratch, variant=self.variant)
+        self.ctx.timer_stop(5)
+        ms = self.ctx.timer_ms(5) / iters
+        scratch.free()
+        return ms
 
     def level_bytes(self, j: int) -> float:
         st = self.levels[j]

@@ -1,0 +1,375 @@
+"""Multi-GPU arrow SpMM: one process per GPU, block-rows of every level sharded across GPUs.
+
+The reference distributes an arrow matrix by giving rank ``i`` the blocks ``A_0i``, ``A_ii``, ``A_i0``
+(``arrow/arrow_slim_mpi.py:246-256``), broadcasting the head features ``X_0`` (``:273``), reducing the
+head result ``C_0 = sum_i A_0i X_i`` to rank 0 (``:116``) and moving rows between consecutive levels with
+all-to-all-v (``arrow/arrow_dec_mpi.py:404-440, 507-550``).  The same algebra here, with a GPU owning a
+contiguous *range* of block-rows of every level:
+
+* local matrix of GPU g at a level  = [ rows 0..w of the level restricted to g's columns ]   (partial C_0)
+                                       [ g's own block-rows (columns: head + own diagonal)   ]
+  in local column numbering ``[head tile | own rows]`` -- ONE SpMM launch per level per GPU;
+* ``X_0`` broadcast  -> every GPU copies the head tile out of GPU 0's memory (NVLink peer read);
+* ``C_0`` reduce     -> GPU 0 pulls the partial head tiles of its peers and adds them;
+* level exchange     -> the owner of a destination row pulls the source row from the peer that owns it
+                        (``arrow_gather_rows_multi``: forward with ``to_prev``, backward -- as a gather-add --
+                        with ``to_next``); the maps are injective, so there are no atomics and no packing;
+* ordering           -> device-side barriers over peer-mapped flags (``arrow_peer_barrier``), no host sync.
+
+``ShardPlan`` is pure numpy (testable anywhere); the engine drives a backend: ``CudaPeerBackend`` (NVLink
+peer memory through CUDA IPC) here, a gloo/numpy stand-in in ``tests/`` for the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import decomp
+
+
+# ------------------------------------------------------------------------------------------------------
+# host-side plan
+# ------------------------------------------------------------------------------------------------------
+class LevelShard:
+    """Rank-local view of one level."""
+    __slots__ = ("level", "n_blocks", "rows_global", "bounds", "r0", "r1", "own_rows", "hoff", "local_rows",
+                 "indptr", "indices", "data", "nnz", "dropped", "fwd_map", "bwd_map")
+
+
+class ShardPlan:
+    def __init__(self, decomposition: Sequence[Tuple[decomp.Level, np.ndarray]], width: int, rank: int, world: int,
+                 block_diagonal: bool = True, n_blocks: Optional[Sequence[int]] = None):
+        if not block_diagonal:
+            raise NotImplementedError("sharded execution covers the block-diagonal layout (the reference's slim mode)")
+        self.width, self.rank, self.world = int(width), int(rank), int(world)
+        self.L = len(decomposition)
+        self.n_blocks = [decomp.number_of_blocks(B, width) for B, _ in decomposition] if n_blocks is None \
+            else [int(b) for b in n_blocks]
+        self.perms, self.to_prev, self.to_next, self.sentinel = decomp.prepare_permutations(
+            [p for _, p in decomposition], self.n_blocks, width)
+        self.levels: List[LevelShard] = []
+        w = self.width
+        for j, (B, _) in enumerate(decomposition):
+            nb = self.n_blocks[j]
+            sh = LevelShard()
+            sh.level, sh.n_blocks, sh.rows_global = j, nb, nb * w
+            sh.bounds = decomp.block_partition(nb, world) * w                 # global row bounds per rank
+            sh.r0, sh.r1 = int(sh.bounds[rank]), int(sh.bounds[rank + 1])
+            sh.own_rows = sh.r1 - sh.r0
+            sh.hoff = w if rank > 0 else 0                                    # own rows sit behind the head tile
+            sh.local_rows = sh.hoff + sh.own_rows
+            self._build_local_matrix(sh, B, nb)
+            # exchange maps hold GLOBAL rows of the neighbouring level (or -1)
+            sh.fwd_map = sh.bwd_map = None
+            if j > 0:
+                tp = self.to_prev[j][sh.r0:sh.r1].copy()                      # level j row -> level j-1 row
+                tp[tp >= self.n_blocks[j - 1] * w] = -1
+                sh.fwd_map = tp
+            if j < self.L - 1:
+                tn = self.to_next[j][sh.r0:sh.r1].copy()                      # level j row -> level j+1 row
+                tn[tn >= self.n_blocks[j + 1] * w] = -1
+                sh.bwd_map = tn
+            self.levels.append(sh)
+
+    def _build_local_matrix(self, sh: LevelShard, B, nb: int):
+        w, rank = self.width, self.rank
+        parts_ptr, parts_idx, parts_dat = [], [], []
+        dropped = 0
+        has_data = decomp.level_triplet(B)[0] is not None
+        if rank > 0:
+            # partial head rows: rows [0, w) of the level restricted to this rank's columns
+            ip, idx, dat, d0 = decomp.arrow_rows(B, w, nb, True, 0, min(w, sh.rows_global))
+            dropped += d0 if rank == 0 else 0
+            keep = (idx >= sh.r0) & (idx < sh.r1)
+            rows = np.repeat(np.arange(ip.size - 1, dtype=np.int64), np.diff(ip))
+            cnt = np.bincount(rows[keep], minlength=w)[:w] if keep.any() else np.zeros(w, dtype=np.int64)
+            cnt = np.concatenate([cnt, np.zeros(w - cnt.size, dtype=np.int64)]) if cnt.size < w else cnt
+            parts_ptr.append(cnt)
+            parts_idx.append((idx[keep].astype(np.int64) - sh.r0 + sh.hoff))
+            if has_data:
+                parts_dat.append(dat[keep])
+        if sh.own_rows > 0:
+            ip, idx, dat, d1 = decomp.arrow_rows(B, w, nb, True, sh.r0, sh.r1)
+            dropped += d1
+            idx = idx.astype(np.int64)
+            if rank == 0:
+                # block-row 0 reaches every column: keep this rank's columns only (peers compute the rest)
+                rows = np.repeat(np.arange(ip.size - 1, dtype=np.int64), np.diff(ip))
+                keep = idx < sh.r1
+                cnt = np.bincount(rows[keep], minlength=sh.own_rows)
+                parts_ptr.append(cnt)
+                parts_idx.append(idx[keep])
+                if has_data:
+                    parts_dat.append(dat[keep])
+            else:
+                local = np.where(idx < w, idx, idx - sh.r0 + sh.hoff)
+                assert np.all((idx < w) | ((idx >= sh.r0) & (idx < sh.r1))), "non-arrow entry in an own block-row"
+                parts_ptr.append(np.diff(ip))
+                parts_idx.append(local)
+                if has_data:
+                    parts_dat.append(dat)
+        counts = np.concatenate(parts_ptr) if parts_ptr else np.zeros(0, dtype=np.int64)
+        sh.indptr = np.zeros(sh.local_rows + 1, dtype=np.int64)
+        if counts.size:
+            np.cumsum(counts, out=sh.indptr[1:1 + counts.size])
+            sh.indptr[1 + counts.size:] = sh.indptr[counts.size]
+        sh.indices = (np.concatenate(parts_idx) if parts_idx else np.zeros(0, np.int64)).astype(np.int32)
+        sh.data = np.ascontiguousarray(np.concatenate(parts_dat), dtype=np.float32) if (has_data and parts_dat) else \
+            (np.ones(sh.indices.size, dtype=np.float32) if not has_data else np.zeros(0, np.float32))
+        sh.nnz = int(sh.indptr[-1])
+        sh.dropped = dropped
+
+    def own_bounds(self, level: int) -> np.ndarray:
+        return self.levels[level].bounds
+
+
+# ------------------------------------------------------------------------------------------------------
+# engine
+# ------------------------------------------------------------------------------------------------------
+class ShardedArrowEngine:
+    """Executes a ShardPlan.  ``backend`` supplies device memory, kernels, peer access and barriers."""
+
+    def __init__(self, plan: ShardPlan, k: int, backend):
+        self.plan, self.k, self.be = plan, int(k), backend
+        self.rank, self.world, self.width, self.L = plan.rank, plan.world, plan.width, plan.L
+        self.mode = "exchange-p2p"
+        be = backend
+        self.mats, self.fwd, self.bwd = [], [], []
+        for sh in plan.levels:
+            self.mats.append(be.csr_upload(sh.local_rows, sh.local_rows, sh.indptr, sh.indices, sh.data)
+                             if sh.local_rows > 0 else None)
+            prev_rows = plan.levels[sh.level - 1].rows_global if sh.level > 0 else 0
+            next_rows = plan.levels[sh.level + 1].rows_global if sh.level < self.L - 1 else 0
+            self.fwd.append(be.map_upload(sh.fwd_map, prev_rows) if sh.fwd_map is not None else None)
+            self.bwd.append(be.map_upload(sh.bwd_map, next_rows) if sh.bwd_map is not None else None)
+        # two ping-pong tiles per level, shared with the peers
+        self.tiles = be.alloc_shared_tiles([max(sh.local_rows, 1) for sh in plan.levels], self.k)
+        self.xi = [0] * self.L
+        self.ci = [0] * self.L
+        self.total_nnz_local = sum(sh.nnz for sh in plan.levels)
+        self.total_nnz = int(be.allreduce_sum(self.total_nnz_local))
+        self.local_rows = plan.levels[0].own_rows
+        be.barrier()
+
+    # -- features / results: this rank's own rows of level 0 ------------------------------------------------
+    def set_features(self, X: np.ndarray, sync: bool = True):
+        sh = self.plan.levels[0]
+        if X.shape != (sh.own_rows, self.k):
+            raise ValueError(f"rank {self.rank}: expected features of shape {(sh.own_rows, self.k)}, got {X.shape}")
+        if self.xi[0] == self.ci[0]:
+            self.xi[0] = 1 - self.ci[0]
+        self.be.h2d(self.tiles[0][self.xi[0]], sh.hoff, X)
+        if sync:
+            self.be.sync()
+
+    def rewind_features(self):
+        if self.xi[0] == self.ci[0]:
+            self.xi[0] = 1 - self.ci[0]
+
+    def result(self, level: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        sh = self.plan.levels[level]
+        return self.be.d2h(self.tiles[level][self.ci[level]], sh.hoff, sh.own_rows, out)
+
+    # -- the iteration -----------------------------------------------------------------------------------------
+    def propagate_features(self):
+        be, pl = self.be, self.plan
+        be.barrier()                                            # every rank's level-0 features are in place
+        for j in range(1, self.L):
+            sh, prev = pl.levels[j], pl.levels[j - 1]
+            if sh.own_rows > 0:
+                # C_i[perm] = recvbuf (arrow_dec_mpi.py:544): pull each routed row from the GPU that owns it
+                be.pull_rows(dst=(j, self.ci[j]), dst_off=sh.hoff, src=(j - 1, self.xi[j - 1]), src_bounds=prev.bounds,
+                             row_map=self.fwd[j], accumulate=False)
+            self.xi[j] = self.ci[j]                             # set_features(C_i) (:545)
+            be.barrier()
+        # X_0 broadcast of every level (arrow_slim_mpi.py:273): copy GPU 0's head tile
+        if self.rank > 0:
+            for j in range(self.L):
+                hr = min(self.width, pl.levels[j].rows_global)
+                be.copy_from_peer(dst=(j, self.xi[j]), dst_off=0, peer=0, src=(j, self.xi[j]), src_off=0, rows=hr)
+
+    def spmm(self):
+        for j in range(self.L):
+            out = 1 - self.xi[j]
+            if self.mats[j] is not None and self.plan.levels[j].local_rows > 0:
+                self.be.spmm(self.mats[j], self.tiles[j][self.xi[j]], self.tiles[j][out])
+            self.ci[j] = out
+
+    def aggregate(self):
+        be, pl = self.be, self.plan
+        be.barrier()                                            # all partial head tiles are written
+        if self.rank == 0:
+            # C_0 = sum_i A_0i X_i (Reduce to rank 0, arrow_slim_mpi.py:116): add the peers' partial head tiles
+            for j in range(self.L):
+                hr = min(self.width, pl.levels[j].rows_global)
+                for g in range(1, self.world):
+                    be.add_from_peer(dst=(j, self.ci[j]), peer=g, src=(j, self.ci[j]), rows=hr)
+        be.barrier()
+        for j in range(self.L - 1, 0, -1):
+            prev, sh = pl.levels[j - 1], pl.levels[j]
+            if prev.own_rows > 0:
+                # C_{j-1}[to_prev[r]] += C_j[r] as a gather-add over this rank's level j-1 rows (:437)
+                be.pull_rows(dst=(j - 1, self.ci[j - 1]), dst_off=prev.hoff, src=(j, self.ci[j]), src_bounds=sh.bounds,
+                             row_map=self.bwd[j - 1], accumulate=True)
+            self.xi[j - 1] = self.ci[j - 1]                     # set_features(C_i) (:438)
+            if j > 1:
+                be.barrier()
+
+    def step(self):
+        self.propagate_features()
+        self.spmm()
+        self.aggregate()
+
+    # -- accounting ----------------------------------------------------------------------------------------------
+    def flops_per_step(self) -> float:
+        return 2.0 * self.total_nnz * self.k
+
+    def algorithmic_bytes_per_step(self) -> float:
+        total = 0.0
+        pl = self.plan
+        for j in range(self.L):
+            rows = pl.levels[j].rows_global
+            total += (rows + 1) * 4 + 2.0 * rows * self.k * 4
+            if j > 0:
+                m = int(np.count_nonzero(pl.to_prev[j][:rows] < pl.levels[j - 1].rows_global))
+                total += 5.0 * m * self.k * 4
+        return total + 8.0 * self.total_nnz
+
+    @property
+    def ctx(self):
+        return self.be.ctx
+
+
+# ------------------------------------------------------------------------------------------------------
+# CUDA backend: NVLink peer memory through CUDA IPC
+# ------------------------------------------------------------------------------------------------------
+class CudaPeerBackend:
+    def __init__(self, comm, device: int, width: int, stream: Optional[int] = None):
+        from . import _lib
+        self.width = int(width)
+        self._lib = _lib
+        self.comm = comm
+        self.rank, self.world = comm.Get_rank(), comm.Get_size()
+        self.ctx = _lib.Context(device, stream)
+        self._tiles = None
+        self._peer = None         # [rank][level][which] -> Dense (imported or own)
+        self._flags = None
+        self._ident = {}
+
+    def csr_upload(self, n_rows, n_cols, indptr, indices, data):
+        return self.ctx.csr_upload(n_rows, n_cols, indptr, indices, data)
+
+    def map_upload(self, m, limit):
+        return self.ctx.map_upload(m, limit)
+
+    def alloc_shared_tiles(self, rows_per_level: Sequence[int], k: int):
+        """One arena per rank (a single cudaMalloc => a single IPC handle): two ping-pong tiles per level + flags."""
+        ctx = self.ctx
+        self.k = k
+        align = 64                                              # floats (256 bytes)
+        offs, pos = [], 64                                      # first 64 floats: barrier flags
+        for r in rows_per_level:
+            pair = []
+            for _ in range(2):
+                pair.append(pos)
+                pos += -(-(r * k) // align) * align
+            offs.append(pair)
+        arena_rows = max(-(-pos // 64), (2 << 20) // 256)       # >= 2 MiB so the driver gives it its own block
+        self._arena = ctx.dense_alloc(arena_rows, 64)
+        ctx.sync()
+        mine = dict(handle=self._arena.ipc_export(), arena_rows=arena_rows, offs=offs, rows=list(rows_per_level))
+        everyone = self.comm.allgather(mine)
+        self._peer, self._flags = [], []
+        for g, info in enumerate(everyone):
+            arena = self._arena if g == self.rank else ctx.ipc_import(info["handle"], info["arena_rows"], 64)
+            base = arena.device_ptr()
+            self._flags.append(ctx.dense_wrap(base, 1, 64))
+            self._peer.append([[ctx.dense_wrap(base + o * 4, r, k) for o in pair] for pair, r in zip(info["offs"], info["rows"])])
+            if g != self.rank:
+                self._imported = getattr(self, "_imported", []) + [arena]
+        self._tiles = self._peer[self.rank]
+        self._views = {}
+        return self._tiles
+
+    def _view(self, g: int, level: int, which: int, off: int, rows: int):
+        """Dense handle on rows [off, off+rows) of a (peer) tile."""
+        key = (g, level, which, off, rows)
+        v = self._views.get(key)
+        if v is None:
+            base = self._peer[g][level][which]
+            v = self.ctx.dense_wrap(base.device_ptr() + off * self.k * 4, rows, self.k)
+            self._views[key] = v
+        return v
+
+    def h2d(self, tile, off, X):
+        tile.h2d(X, row0=off)
+
+    def d2h(self, tile, off, rows, out=None):
+        return tile.d2h(out, row0=off, rows=rows)
+
+    def sync(self):
+        self.ctx.sync()
+
+    def barrier(self):
+        if self.world > 1:
+            self.ctx.peer_barrier(self._flags, self.rank)
+
+    def allreduce_sum(self, v):
+        return sum(self.comm.allgather(int(v)))
+
+    def spmm(self, A, X, C):
+        self.ctx.spmm(A, X, C)
+
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate):
+        lvl, which = dst
+        n = row_map.n
+        d = self._view(self.rank, lvl, which, dst_off, n)
+        srcs = []
+        for g in range(self.world):
+            own = int(src_bounds[g + 1] - src_bounds[g])
+            hoff = self._hoff(g)
+            srcs.append(self._view(g, src[0], src[1], hoff if own > 0 else 0, max(own, 0)))
+        self.ctx.gather_rows_multi(d, srcs, [int(b) for b in src_bounds], row_map, accumulate=accumulate)
+
+    def _hoff(self, g: int) -> int:
+        return self.width if g > 0 else 0
+
+    def copy_from_peer(self, dst, dst_off, peer, src, src_off, rows):
+        d = self._view(self.rank, dst[0], dst[1], dst_off, rows)
+        s = self._view(peer, src[0], src[1], src_off, rows)
+        d.copy_from(s, rows=rows)
+
+    def add_from_peer(self, dst, peer, src, rows):
+        d = self._view(self.rank, dst[0], dst[1], 0, rows)
+        s = self._view(peer, src[0], src[1], 0, rows)
+        ident = self._ident.get(rows)
+        if ident is None:
+            ident = self.ctx.map_upload(np.arange(rows, dtype=np.int64), rows)
+            self._ident[rows] = ident
+        self.ctx.gather_rows(d, s, ident, accumulate=True)
+
+
+class ShardedArrowDecomposition:
+    """Convenience wrapper used by bench.py at N > 1: plan + CUDA peer backend + the reference-like calls."""
+
+    def __init__(self, comm, decomposition, width: int, k: int, device: int = 0):
+        self.comm = comm
+        plan = ShardPlan(decomposition, width, comm.Get_rank(), comm.Get_size())
+        be = CudaPeerBackend(comm, device, width)
+        self.engine = ShardedArrowEngine(plan, k, be)
+        self.B = self
+        self.matrix_index = 0
+        self.decomposition_length = plan.L
+
+    def set_features(self, X):
+        self.engine.set_features(np.ascontiguousarray(X, dtype=np.float32))
+
+    def result_tile(self, out=None):
+        return self.engine.result(0, out)
+
+    def step(self):
+        self.engine.step()
+
+    def synchronize(self):
+        self.engine.be.sync()

@@ -123,9 +123,10 @@ int  arrow_gather_rows_multi(arrow_ctx *ctx, int dst_buf, const int *src_bufs,
                              const int64_t *row_bounds, int n_src, int map, int flags);
 
 /* ---- cross-process peer memory (one process per GPU; NVLink P2P through CUDA IPC) -------------- */
-#define ARROW_IPC_HANDLE_BYTES 64
-int  arrow_ipc_export(arrow_ctx *ctx, int buf, void *handle64);
-int  arrow_ipc_import(arrow_ctx *ctx, const void *handle64, int64_t rows, int k, int *buf_out);
+/* handle = 64-byte cudaIpcMemHandle_t + 8-byte offset of the tile inside the exported allocation + padding */
+#define ARROW_IPC_HANDLE_BYTES 80
+int  arrow_ipc_export(arrow_ctx *ctx, int buf, void *handle);
+int  arrow_ipc_import(arrow_ctx *ctx, const void *handle, int64_t rows, int k, int *buf_out);
 /* Device-side barrier across `world` ranks over peer-mapped flag words (no host sync, no NCCL):
  * flags_buf[s] is rank s's flag tile (>= world floats... see DESIGN.md), my slot = rank. */
 int  arrow_peer_barrier(arrow_ctx *ctx, const int *flag_bufs, int rank, int world);

@@ -1,0 +1,81 @@
+"""Test double for the sharded engine's backend: numpy/scipy tiles, gloo for the peers (CPU only).
+
+Peer memory is emulated faithfully to the protocol's own rule -- a rank may only read peer data that
+was final before the last barrier: at every ``barrier()`` each rank publishes a snapshot of its tiles
+(all_gather over gloo) and remote reads are served from the snapshots.  A missing barrier in the engine
+therefore shows up as a stale read and a failing test.
+"""
+import numpy as np
+from scipy import sparse
+
+
+class _Map:
+    def __init__(self, m, limit):
+        m = np.asarray(m, dtype=np.int64)
+        self.m = np.where((m < 0) | (m >= limit), -1, m)
+        self.n = m.size
+
+
+class GlooNumpyBackend:
+    def __init__(self, comm, width):
+        self.comm, self.width = comm, width
+        self.rank, self.world = comm.Get_rank(), comm.Get_size()
+        self.ctx = None
+        self.snap = None
+        self.n_barriers = 0
+
+    def csr_upload(self, n_rows, n_cols, indptr, indices, data):
+        return sparse.csr_matrix((data, indices, indptr), shape=(n_rows, n_cols), dtype=np.float32)
+
+    def map_upload(self, m, limit):
+        return _Map(m, limit)
+
+    def alloc_shared_tiles(self, rows_per_level, k):
+        self.k = k
+        self.tiles = [[np.zeros((r, k), np.float32), np.zeros((r, k), np.float32)] for r in rows_per_level]
+        return self.tiles
+
+    def h2d(self, tile, off, X):
+        tile[off:off + X.shape[0]] = X
+
+    def d2h(self, tile, off, rows, out=None):
+        if out is None:
+            return tile[off:off + rows].copy()
+        out[:] = tile[off:off + rows]
+        return out
+
+    def sync(self):
+        pass
+
+    def barrier(self):
+        self.snap = self.comm.allgather([[t.copy() for t in pair] for pair in self.tiles])
+        self.n_barriers += 1
+
+    def allreduce_sum(self, v):
+        return sum(self.comm.allgather(int(v)))
+
+    def spmm(self, A, X, C):
+        C[:] = A @ X
+
+    def _tile(self, g, level, which):
+        return self.tiles[level][which] if g == self.rank else self.snap[g][level][which]
+
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate):
+        d = self.tiles[dst[0]][dst[1]]
+        m = row_map.m
+        for g in range(self.world):
+            sel = np.flatnonzero((m >= src_bounds[g]) & (m < src_bounds[g + 1]))
+            if sel.size == 0:
+                continue
+            hoff = self.width if g > 0 else 0
+            rows = self._tile(g, src[0], src[1])[hoff + m[sel] - src_bounds[g]]
+            if accumulate:
+                d[dst_off + sel] += rows
+            else:
+                d[dst_off + sel] = rows
+
+    def copy_from_peer(self, dst, dst_off, peer, src, src_off, rows):
+        self.tiles[dst[0]][dst[1]][dst_off:dst_off + rows] = self._tile(peer, src[0], src[1])[src_off:src_off + rows]
+
+    def add_from_peer(self, dst, peer, src, rows):
+        self.tiles[dst[0]][dst[1]][:rows] += self._tile(peer, src[0], src[1])[:rows]

@@ -1,0 +1,88 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box): one process per GPU, NVLink peer memory through CUDA IPC."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+        from arrow_matrix_b200 import synth
+        from arrow_matrix_b200.comm import world_comm
+        from arrow_matrix_b200.sharded import ShardedArrowDecomposition
+        from oracle import oracle
+        w, t0, k, levels, nested = {"L2k128": (128, 9, 128, 2, True), "L3k16": (64, 11, 16, 3, True),
+                                    "L3stale_k6": (32, 6, 6, 3, False)}[case]
+        dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600)
+        arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank)
+        eng = arrow.engine
+        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        rng = np.random.default_rng(2)
+        sh0 = eng.plan.levels[0]
+        for it in range(3):
+            X = synth.generate_dense_matrix(t0 * w, k, np.float32, rng)
+            if it != 1:                                     # iteration 1 is chained (X := A X)
+                arrow.B.set_features(X[sh0.r0:sh0.r1])
+                po.set_features(X.copy())
+            arrow.step()
+            po.step()
+            for j in range(eng.L):
+                sh = eng.plan.levels[j]
+                got = eng.result(j)
+                ref = po.C[j][sh.r0:sh.r1]
+                scale = max(float(np.max(np.abs(po.C[j]))), 1e-30)
+                err = float(np.max(np.abs(got - ref))) if ref.size else 0.0
+                assert err <= 2e-5 * scale, (case, rank, it, j, err, scale)
+            po.C[0][sh0.r0:sh0.r1] = eng.result(0)          # keep the chained iteration from compounding rounding
+        arrow.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except BaseException:     # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6"])
+def test_sharded_engine_on_gpus(case):
+    import torch.multiprocessing as mp
+    world = min(_n_gpus(), 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    bad = [f"rank {r}: {m}" for r, m in sorted(results) if m != "ok"]
+    assert not bad, "\n".join(bad)

@@ -1,0 +1,106 @@
+"""CPU tests of the multi-GPU path's host logic: world_size 2 and 3 over gloo, numpy tiles.
+
+Each rank builds its ShardPlan, runs ShardedArrowEngine.step() on the gloo/numpy backend and compares
+its own rows with the protocol oracle (which itself is pinned against the real reference)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, case, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        from arrow_matrix_b200 import synth
+        from arrow_matrix_b200.comm import TorchComm, world_comm
+        from arrow_matrix_b200.sharded import ShardPlan, ShardedArrowEngine
+        from oracle import oracle
+        from tests.numpy_backend import GlooNumpyBackend
+        comm = world_comm()
+        assert isinstance(comm, TorchComm) and comm.Get_size() == world and comm.Get_rank() == rank
+        if case.startswith("golden:"):
+            from tests.golden_util import GoldenCase
+            g = GoldenCase(case.split(":", 1)[1])
+            dec, w, k = g.decomposition, g.width, g.k
+            Xs = g.X
+        else:
+            w, t0, k, levels, kind, nested = {"L2": (16, 7, 8, 2, "random", True), "L3": (8, 9, 5, 3, "random", True),
+                                              "L3stale": (8, 6, 4, 3, "random", False), "small": (8, 2, 4, 2, "random", True)}[case]
+            dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind=kind, seed=77, nested=nested, hub_rows=2, hub_nnz=40)
+            rng = np.random.default_rng(5)
+            n0 = t0 * w
+            Xs = [synth.generate_dense_matrix(n0, k, np.float32, rng), None, synth.generate_dense_matrix(n0, k, np.float32, rng)]
+        plan = ShardPlan(dec, w, rank, world)
+        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w))
+        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        assert eng.total_nnz == sum(M.nnz for M in po.mats)
+        sh0 = plan.levels[0]
+        for it, X in enumerate(Xs):
+            if X is not None:
+                eng.set_features(X[sh0.r0:sh0.r1])
+                po.set_features(X.copy())
+            eng.step()
+            po.step()
+            for j in range(plan.L):
+                sh = plan.levels[j]
+                got = eng.result(j)
+                assert got.shape == (sh.own_rows, k)
+                assert np.allclose(got, po.C[j][sh.r0:sh.r1], rtol=1e-5, atol=1e-5), (case, rank, it, j)
+        assert comm.allreduce_lor(False) is False
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except BaseException as e:     # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", ["L2", "L3", "L3stale", "small", "golden:slim_L2_random_k4", "golden:slim_L3_nonnested_k3"])
+def test_sharded_engine_over_gloo(world, case):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(30)
+    bad = [f"rank {rank}: {msg}" for rank, msg in sorted(results) if msg != "ok" and "Connection closed by peer" not in msg]
+    bad = bad or [f"rank {rank}: {msg}" for rank, msg in sorted(results) if msg != "ok"]
+    assert not bad, "\n".join(bad)
+
+
+def test_shard_plan_covers_the_matrix():
+    """the local matrices of all ranks together hold every arrow entry exactly once"""
+    sys.path.insert(0, ROOT)
+    from arrow_matrix_b200 import synth
+    from arrow_matrix_b200.sharded import ShardPlan
+    w, t0 = 8, 7
+    dec = synth.synth_decomposition(t0, w, levels=2, seed=3, hub_rows=2, hub_nnz=30)
+    for world in (1, 2, 4, 8, 16):
+        tot = [0, 0]
+        for r in range(world):
+            pl = ShardPlan(dec, w, r, world)
+            for j in range(2):
+                tot[j] += pl.levels[j].nnz
+                assert pl.levels[j].indices.size == pl.levels[j].nnz
+                if pl.levels[j].nnz:
+                    assert pl.levels[j].indices.max() < pl.levels[j].local_rows
+        assert tot == [dec[0][0].nnz, dec[1][0].nnz], (world, tot)
