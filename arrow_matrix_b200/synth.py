@@ -51,7 +51,7 @@ def _stratified(rng: np.random.Generator, n_rows: int, draws: int, lo: np.ndarra
 
 def arrow_csr(n_total: int, width: int, n_active_blocks: int, rng: np.random.Generator,
               head_nnz: int = 3, diag_nnz: int = 7, dtype=np.float32,
-              hub_rows: int = 0, hub_nnz: int = 0) -> sparse.csr_matrix:
+              hub_rows: int = 0, hub_nnz: int = 0, band_nnz: int = 0) -> sparse.csr_matrix:
     """Arrow-shaped ``n_total x n_total`` CSR whose first ``n_active_blocks*width`` rows are non-empty.
 
     Block-row 0 spreads ``head_nnz+diag_nnz`` entries over all active columns; block-row ``i>0``
@@ -95,6 +95,22 @@ def arrow_csr(n_total: int, width: int, n_active_blocks: int, rng: np.random.Gen
                           shape=(n_total, n_total), dtype=dtype)
     m.has_sorted_indices = True
     m.has_canonical_format = True
+    if band_nnz > 0 and n_active_blocks > 2:
+        # banded (non block-diagonal) variant: extra entries in the neighbouring blocks (i, i-1) and (i, i+1)
+        # for block-rows i >= 1 (the reference's arrow-banded shape, arrow_mpi.py:211-219)
+        rows = np.repeat(np.arange(width, n_act, dtype=np.int64), band_nnz)
+        bi = rows // width
+        side = rng.integers(0, 2, size=rows.size) * 2 - 1
+        bj = bi + side
+        bj = np.where(bj < 1, bi + 1, bj)
+        bj = np.where(bj >= n_active_blocks, bi - 1, bj)
+        ok = (bj >= 1) & (bj < n_active_blocks) & (bj != bi)
+        cols = bj * width + rng.integers(0, width, size=rows.size)
+        extra = sparse.csr_matrix((rng.random(int(ok.sum()), dtype=dtype), (rows[ok], cols[ok])),
+                                  shape=(n_total, n_total), dtype=dtype)
+        m = sparse.csr_matrix(m + extra)
+        m.sum_duplicates()
+        m.sort_indices()
     return m
 
 
@@ -116,7 +132,7 @@ def make_permutation(n: int, kind: str, rng: np.random.Generator, shards: int = 
 
 def synth_decomposition(n_blocks0: int, width: int, levels: int = 2, perm_kind: str = "random",
                         seed: int = 503, shrink: int = 2, hub_rows: int = 0, hub_nnz: int = 0,
-                        head_nnz: int = 3, diag_nnz: int = 7, nested: bool = True,
+                        head_nnz: int = 3, diag_nnz: int = 7, nested: bool = True, band_nnz: int = 0,
                         ) -> List[Tuple[sparse.csr_matrix, np.ndarray]]:
     """G2 of SURVEY.md 8d: ``levels`` arrow matrices over ``n = n_blocks0*width`` vertices.
 
@@ -136,7 +152,7 @@ def synth_decomposition(n_blocks0: int, width: int, levels: int = 2, perm_kind: 
     for j in range(levels):
         act = max(1, n_blocks0 // (shrink ** j))
         mat = arrow_csr(n, width, act, rng, head_nnz=head_nnz, diag_nnz=diag_nnz,
-                        hub_rows=hub_rows if j == 0 else 0, hub_nnz=hub_nnz)
+                        hub_rows=hub_rows if j == 0 else 0, hub_nnz=hub_nnz, band_nnz=band_nnz)
         perm = make_permutation(n, "identity" if j == 0 else perm_kind, rng)
         if nested and j >= 2:
             # re-draw so that positions [0, prev_act) of this level stay inside the previous level's active rows

@@ -202,6 +202,7 @@ class ReferenceProtocolOracle:
         self.X = [np.zeros((r, k), dtype=np.float32) for r in self.rows]
         self._mm = csr_spmm_c if use_c_kernel else (lambda A, X: A @ X)
         self.blockwise = blockwise
+        self.block_diagonal = block_diagonal
 
     def set_features(self, X0: np.ndarray) -> None:
         """Level-0 tiles, in level-0 (permuted) row order; stored by reference like ``set_features``."""
@@ -231,6 +232,11 @@ class ReferenceProtocolOracle:
         for i in range(1, t):
             ci = M[i * w:(i + 1) * w, i * w:(i + 1) * w] @ X[i * w:(i + 1) * w]
             ci += M[i * w:(i + 1) * w, :w] @ X0
+            if not self.block_diagonal:                     # banded layout, arrow_mpi.py:211-219
+                if i > 1:
+                    ci += M[i * w:(i + 1) * w, (i - 1) * w:i * w] @ X[(i - 1) * w:i * w]
+                if i < t - 1:
+                    ci += M[i * w:(i + 1) * w, (i + 1) * w:(i + 2) * w] @ X[(i + 1) * w:(i + 2) * w]
             out[i * w:(i + 1) * w] = ci
         return out
 

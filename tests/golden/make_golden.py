@@ -158,6 +158,13 @@ def main():
     dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=404)
     save_case("wide_L2_random_k5", dec, w, k, False, True, [feats(t0 * w, k), None])
 
+    # G: wide layout, BANDED (non block-diagonal): blocks (i, i-1), (i, i+1) and the neighbour tile exchange
+    #    (arrow_mpi.py:123-175, 211-219)
+    w, t0, k = 8, 5, 4
+    dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=707, band_nnz=3, shrink=1)
+    save_case("wide_L2_banded_k4", dec, w, k, False, False, [feats(t0 * w, k), feats(t0 * w, k)],
+              note="non block-diagonal: A_i,i-1 and A_i,i+1 present")
+
     # E: Julia-converter quirks: no data file (ones), int64 indices, 1-based permutations
     w, t0, k = 8, 4, 4
     dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=505)
