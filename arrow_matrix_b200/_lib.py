@@ -27,6 +27,8 @@ EXPORTS = [
     "arrow_map_upload", "arrow_map_free", "arrow_map_compose", "arrow_map_invert", "arrow_map_d2h",
     "arrow_dense_alloc", "arrow_dense_free", "arrow_dense_fill", "arrow_dense_h2d", "arrow_dense_d2h",
     "arrow_dense_copy", "arrow_dense_ptr", "arrow_dense_wrap", "arrow_host_alloc", "arrow_host_free",
+    "arrow_dense_h2d_lane", "arrow_dense_d2h_lane", "arrow_lane_wait", "arrow_lane_sync",
+    "arrow_event_record", "arrow_event_wait",
     "arrow_spmm", "arrow_gather_rows", "arrow_gather_rows_multi",
     "arrow_ipc_export", "arrow_ipc_import", "arrow_peer_barrier",
     "arrow_timer_start", "arrow_timer_stop", "arrow_timer_elapsed_ms", "arrow_launch_count", "arrow_l2_flush",
@@ -81,6 +83,12 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         "arrow_dense_copy": (c_int, [P, I, I64, I, I64, I64]),
         "arrow_dense_ptr": (c_int, [P, I, POINTER(P), pI64, pI]),
         "arrow_dense_wrap": (c_int, [P, P, I64, I, pI]),
+        "arrow_dense_h2d_lane": (c_int, [P, I, I, I64, I64, P]),
+        "arrow_dense_d2h_lane": (c_int, [P, I, I, I64, I64, P]),
+        "arrow_lane_wait": (c_int, [P, I, I]),
+        "arrow_lane_sync": (c_int, [P, I]),
+        "arrow_event_record": (c_int, [P, I, I]),
+        "arrow_event_wait": (c_int, [P, I, I]),
         "arrow_host_alloc": (c_int, [c_size_t, POINTER(P)]),
         "arrow_host_free": (c_int, [P]),
         "arrow_spmm": (c_int, [P, I, I, I, I, I, I]),
@@ -253,6 +261,29 @@ class Context:
         n = len(flag_tiles)
         hs = (c_int * n)(*[s.h for s in flag_tiles])
         self._check(self.lib.arrow_peer_barrier(self._h, hs, int(rank), n))
+
+    # -- copy lanes -------------------------------------------------------------------------
+    LANE_MAIN, LANE_H2D, LANE_D2H = 0, 1, 2
+
+    def h2d_lane(self, lane: int, dst: "Dense", X: np.ndarray, row0: int = 0):
+        assert X.dtype == np.float32 and X.flags.c_contiguous and X.shape[1] == dst.k
+        self._check(self.lib.arrow_dense_h2d_lane(self._h, lane, dst.h, int(row0), X.shape[0], _ptr(X)))
+
+    def d2h_lane(self, lane: int, src: "Dense", out: np.ndarray, row0: int = 0):
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape[1] == src.k
+        self._check(self.lib.arrow_dense_d2h_lane(self._h, lane, src.h, int(row0), out.shape[0], _ptr(out)))
+
+    def lane_wait(self, waiting_lane: int, signalling_lane: int):
+        self._check(self.lib.arrow_lane_wait(self._h, waiting_lane, signalling_lane))
+
+    def lane_sync(self, lane: int):
+        self._check(self.lib.arrow_lane_sync(self._h, lane))
+
+    def event_record(self, event: int, lane: int):
+        self._check(self.lib.arrow_event_record(self._h, event, lane))
+
+    def event_wait(self, event: int, lane: int):
+        self._check(self.lib.arrow_event_wait(self._h, event, lane))
 
     # -- timing -----------------------------------------------------------------------------
     def timer_start(self, slot: int = 0):

@@ -114,8 +114,17 @@ class ArrowDecompositionMPI:
         eng.aggregate()
         wb_logging.log({"spmm_reduce_time": time.perf_counter() - tic})
 
+    def step_stream(self, X_host: np.ndarray, out_host: np.ndarray):
+        """Extension for host-resident features: enqueue ``set_features(X); step(); result_tile(out)`` so that
+        uploads, compute and downloads of consecutive iterations overlap (see ``ArrowEngine.stream_step``).
+        Call ``synchronize()`` before reading ``out_host``."""
+        self._require_engine().stream_step(X_host, out_host)
+
     def synchronize(self):
-        self._require_engine().ctx.sync()
+        eng = self._require_engine()
+        if hasattr(eng, "_slots"):
+            eng.stream_drain()
+        eng.ctx.sync()
 
     def _to_exchange_mode(self):
         """Materialise per-level tiles (needed to observe levels > 0): re-runs nothing, keeps level-0 tiles."""

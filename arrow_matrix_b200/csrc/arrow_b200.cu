@@ -101,6 +101,9 @@ struct arrow_ctx {
     size_t flush_bytes = 0;
     unsigned int barrier_epoch = 0;
     int *dev_status = nullptr;        // device-side status word (barrier timeout)
+    cudaStream_t lanes[ARROW_N_LANES] = {nullptr, nullptr, nullptr};   // lane 0 = main stream
+    cudaEvent_t lane_events[ARROW_N_LANES] = {nullptr, nullptr, nullptr};
+    cudaEvent_t user_events[ARROW_MAX_EVENTS] = {};
 };
 
 namespace {
@@ -1042,6 +1045,12 @@ void arrow_ctx_destroy(arrow_ctx *ctx) {
     if (ctx->long_scratch) cudaFree(ctx->long_scratch);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->dev_status) cudaFree(ctx->dev_status);
+    for (int l = 1; l < ARROW_N_LANES; ++l)
+        if (ctx->lanes[l]) { cudaStreamSynchronize(ctx->lanes[l]); cudaStreamDestroy(ctx->lanes[l]); }
+    for (int l = 0; l < ARROW_N_LANES; ++l)
+        if (ctx->lane_events[l]) cudaEventDestroy(ctx->lane_events[l]);
+    for (int e = 0; e < ARROW_MAX_EVENTS; ++e)
+        if (ctx->user_events[e]) cudaEventDestroy(ctx->user_events[e]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1746,6 +1755,85 @@ int arrow_peer_barrier(arrow_ctx *ctx, const int *flag_bufs, int rank, int world
     k_peer_barrier<<<1, 32, 0, ctx->stream>>>(pf, rank, world, ctx->barrier_epoch, ctx->dev_status);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    return ARROW_OK;
+}
+
+// ---- copy lanes: host staging on side streams, ordered against the main stream with events ----------
+static int lane_stream(arrow_ctx *ctx, int lane, cudaStream_t *out) {
+    if (lane < 0 || lane >= ARROW_N_LANES) return fail(ctx, ARROW_ERR_ARG, "lane %d out of range", lane);
+    if (lane == ARROW_LANE_MAIN) { *out = ctx->stream; return ARROW_OK; }
+    if (!ctx->lanes[lane]) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->lanes[lane], cudaStreamNonBlocking));
+    *out = ctx->lanes[lane];
+    return ARROW_OK;
+}
+
+int arrow_dense_h2d_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, const float *host) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
+    if (!host || row0 < 0 || rows < 0 || row0 + rows > d->rows) return fail(ctx, ARROW_ERR_ARG, "h2d range outside tile");
+    cudaStream_t st;
+    int rc = lane_stream(ctx, lane, &st);
+    if (rc != ARROW_OK) return rc;
+    if (rows) CUDA_TRY(ctx, cudaMemcpyAsync(d->p + (size_t)row0 * d->k, host, (size_t)rows * d->k * 4, cudaMemcpyHostToDevice, st));
+    return ARROW_OK;
+}
+
+int arrow_dense_d2h_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, float *host) {
+    CHECK_CTX(ctx);
+    DenseBuf *d = get_dense(ctx, buf);
+    if (!d) return fail(ctx, ARROW_ERR_HANDLE, "bad dense handle %d", buf);
+    if (!host || row0 < 0 || rows < 0 || row0 + rows > d->rows) return fail(ctx, ARROW_ERR_ARG, "d2h range outside tile");
+    cudaStream_t st;
+    int rc = lane_stream(ctx, lane, &st);
+    if (rc != ARROW_OK) return rc;
+    if (rows) CUDA_TRY(ctx, cudaMemcpyAsync(host, d->p + (size_t)row0 * d->k, (size_t)rows * d->k * 4, cudaMemcpyDeviceToHost, st));
+    return ARROW_OK;
+}
+
+int arrow_lane_wait(arrow_ctx *ctx, int waiting_lane, int signalling_lane) {
+    CHECK_CTX(ctx);
+    cudaStream_t w, sgn;
+    int rc = lane_stream(ctx, waiting_lane, &w);
+    if (rc != ARROW_OK) return rc;
+    rc = lane_stream(ctx, signalling_lane, &sgn);
+    if (rc != ARROW_OK) return rc;
+    if (w == sgn) return ARROW_OK;
+    cudaEvent_t &ev = ctx->lane_events[signalling_lane];
+    if (!ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ev, sgn));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(w, ev, 0));
+    return ARROW_OK;
+}
+
+int arrow_event_record(arrow_ctx *ctx, int event, int lane) {
+    CHECK_CTX(ctx);
+    if (event < 0 || event >= ARROW_MAX_EVENTS) return fail(ctx, ARROW_ERR_ARG, "event %d out of range", event);
+    cudaStream_t st;
+    int rc = lane_stream(ctx, lane, &st);
+    if (rc != ARROW_OK) return rc;
+    if (!ctx->user_events[event]) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->user_events[event], cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->user_events[event], st));
+    return ARROW_OK;
+}
+
+int arrow_event_wait(arrow_ctx *ctx, int event, int lane) {
+    CHECK_CTX(ctx);
+    if (event < 0 || event >= ARROW_MAX_EVENTS) return fail(ctx, ARROW_ERR_ARG, "event %d out of range", event);
+    if (!ctx->user_events[event]) return ARROW_OK;            // never recorded: nothing to wait for
+    cudaStream_t st;
+    int rc = lane_stream(ctx, lane, &st);
+    if (rc != ARROW_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->user_events[event], 0));
+    return ARROW_OK;
+}
+
+int arrow_lane_sync(arrow_ctx *ctx, int lane) {
+    CHECK_CTX(ctx);
+    cudaStream_t st;
+    int rc = lane_stream(ctx, lane, &st);
+    if (rc != ARROW_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return ARROW_OK;
 }
 

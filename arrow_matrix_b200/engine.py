@@ -205,6 +205,44 @@ class ArrowEngine:
         self.spmm()
         self.aggregate()
 
+    # -- streaming iteration for host-resident features ------------------------------------------------------
+    def stream_step(self, X_host: np.ndarray, out_host: np.ndarray):
+        """Enqueue one full iteration on host data: upload ``X_host`` -> ``step()`` -> download level-0 result
+        into ``out_host``.  Returns immediately; uploads, compute and downloads of consecutive calls overlap
+        (side copy streams ordered with events, two device slots).  Both arrays must be pinned
+        (``_lib.PinnedArray``) and must stay untouched until ``stream_drain()``; use at least two
+        (X, out) pairs in rotation.  Results are identical to ``set_features(X); step(); result()``."""
+        st = self.levels[0]
+        if X_host.shape != (st.rows, self.k) or out_host.shape != (st.rows, self.k):
+            raise ValueError(f"expected host arrays of shape {(st.rows, self.k)}")
+        ctx = self.ctx
+        if not hasattr(self, "_slots"):
+            # slot 0 re-uses the engine's own level-0 tiles, slot 1 gets two more
+            self._slots = [list(st.bufs), [ctx.dense_alloc(st.rows, self.k), ctx.dense_alloc(st.rows, self.k)]]
+            self._slot_i = 0
+        s = self._slot_i % 2
+        slot = self._slots[s]
+        self._slot_i += 1
+        EV_H2D, EV_MAIN, EV_D2H = 3 * s, 3 * s + 1, 3 * s + 2      # per-slot events
+        ctx.event_wait(EV_MAIN, ctx.LANE_H2D)      # the compute two calls ago has finished reading slot[0]
+        ctx.h2d_lane(ctx.LANE_H2D, slot[0], X_host)
+        ctx.event_record(EV_H2D, ctx.LANE_H2D)
+        ctx.event_wait(EV_H2D, ctx.LANE_MAIN)      # features are on the device
+        ctx.event_wait(EV_D2H, ctx.LANE_MAIN)      # slot[1]'s previous result has been downloaded
+        st.bufs = slot
+        st.xi, st.ci = 0, 1                        # X = uploaded tile, C = the slot's second tile
+        self.step()
+        ctx.event_record(EV_MAIN, ctx.LANE_MAIN)
+        ctx.event_wait(EV_MAIN, ctx.LANE_D2H)
+        ctx.d2h_lane(ctx.LANE_D2H, st.bufs[st.ci], out_host)
+        ctx.event_record(EV_D2H, ctx.LANE_D2H)
+
+    def stream_drain(self):
+        ctx = self.ctx
+        ctx.lane_sync(ctx.LANE_H2D)
+        ctx.sync()
+        ctx.lane_sync(ctx.LANE_D2H)
+
     # -- accounting (SURVEY.md 8d) ------------------------------------------------------------------------
     def flops_per_step(self) -> float:
         return 2.0 * self.total_nnz * self.k

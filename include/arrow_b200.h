@@ -101,6 +101,22 @@ int  arrow_dense_copy(arrow_ctx *ctx, int dst, int64_t dst_row0, int src, int64_
 int  arrow_dense_ptr(arrow_ctx *ctx, int buf, void **device_ptr, int64_t *rows, int *k);
 /* Wrap device memory owned by someone else (a torch tensor, an IPC-imported peer tile). */
 int  arrow_dense_wrap(arrow_ctx *ctx, void *device_ptr, int64_t rows, int k, int *buf_out);
+/* Copy lanes: host<->device staging on side streams so that step i's download, step i+1's upload and the
+ * compute in between overlap (PCIe is full duplex).  Lane 0 is the context's main stream.  arrow_lane_wait
+ * makes `waiting_lane` wait for everything submitted so far on `signalling_lane` (event, no host sync).
+ * Replaces the blocking cp.asarray / cp.asnumpy round trips of arrow_slim_mpi.py:186-191, 228-232. */
+#define ARROW_LANE_MAIN 0
+#define ARROW_LANE_H2D  1
+#define ARROW_LANE_D2H  2
+#define ARROW_N_LANES   3
+int  arrow_dense_h2d_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, const float *host);
+int  arrow_dense_d2h_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, float *host);
+int  arrow_lane_wait(arrow_ctx *ctx, int waiting_lane, int signalling_lane);
+int  arrow_lane_sync(arrow_ctx *ctx, int lane);
+/* Named events for finer ordering between lanes (waiting on a never-recorded event is a no-op). */
+#define ARROW_MAX_EVENTS 16
+int  arrow_event_record(arrow_ctx *ctx, int event, int lane);
+int  arrow_event_wait(arrow_ctx *ctx, int event, int lane);
 /* pinned host staging */
 int  arrow_host_alloc(size_t bytes, void **ptr);
 int  arrow_host_free(void *ptr);
