@@ -101,6 +101,7 @@ struct arrow_ctx {
     size_t flush_bytes = 0;
     unsigned int barrier_epoch = 0;
     int *dev_status = nullptr;        // device-side status word (barrier timeout)
+    int *tile_ticket = nullptr;       // device counter of the dynamic tile scheduler
     cudaStream_t lanes[ARROW_N_LANES] = {nullptr, nullptr, nullptr};   // lane 0 = main stream
     cudaEvent_t lane_events[ARROW_N_LANES] = {nullptr, nullptr, nullptr};
     cudaEvent_t user_events[ARROW_MAX_EVENTS] = {};
@@ -528,6 +529,7 @@ struct TileArgs {
     const int4 *__restrict__ tiles;
     int n_tiles;
     int skip;            // indices may hold -1
+    int *ticket;         // dynamic tile scheduler (zeroed before the launch)
 };
 
 template <int G, int VPL, bool ROWMAP, bool ACC>
@@ -538,8 +540,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
     const SpmmArgs &a = t.a;
     constexpr int RPW = 32 / G;
     constexpr int UNROLL = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+    constexpr int TAIL = (UNROLL >= 4) ? UNROLL / 2 : UNROLL;     // predicated tail batches
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const bool EXACT = (t.a.k4 == G * VPL);                       // every lane owns valid columns
     const int gl = lane % G;
     const int gi = lane / G;
     const int k4 = a.k4;
@@ -568,13 +572,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
         }
     };
 
+    // Dynamic scheduling: the first tile is blockIdx.x, every further tile comes from an atomic ticket.  All CTAs
+    // therefore work on one compact, moving window of ~gridDim.x consecutive tiles; a static round-robin lets
+    // CTAs drift apart over the ~260 tiles each one processes at 10M rows and the live X panels fall out of L2
+    // (measured: 62 % L2 hit rate, DRAM traffic 1.30x algorithmic before this change).
+    __shared__ int s_next[2];
     uint32_t parity0 = 0u, parity1 = 0u;
     int tile = blockIdx.x;
     int st = 0;
     if (tile < t.n_tiles && threadIdx.x == 0) prefetch(tile, 0);
-    for (; tile < t.n_tiles; tile += gridDim.x, st ^= 1) {
-        const int next = tile + gridDim.x;
-        if (next < t.n_tiles && threadIdx.x == 0) prefetch(next, st ^ 1);
+    for (; tile < t.n_tiles; st ^= 1) {
+        if (threadIdx.x == 0) {
+            const int next = atomicAdd(t.ticket, 1) + (int)gridDim.x;
+            s_next[st] = next;
+            if (next < t.n_tiles) prefetch(next, st ^ 1);
+        }
         const int4 d = __ldg(t.tiles + tile);
         if (st == 0) { mbar_wait(&bars[0], parity0); parity0 ^= 1u; }
         else         { mbar_wait(&bars[1], parity1); parity1 ^= 1u; }
@@ -598,25 +610,50 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
             float4 acc[VPL];
 #pragma unroll
             for (int i = 0; i < VPL; ++i) acc[i] = f4_zero();
-            for (int p = s; p < e; p += UNROLL) {
-                int c[UNROLL];
-                float v[UNROLL];
+            int p = s;
+            if (EXACT && !t.skip) {
+                // full batches: no bounds / validity predicates at all (the common case)
+                for (; p + UNROLL <= e; p += UNROLL) {
+                    int c[UNROLL];
+                    float v[UNROLL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
+                    for (int u = 0; u < UNROLL; ++u) {
+                        c[u] = s_idx[p + u];
+                        v[u] = s_val[p + u];
+                    }
+                    float4 x[UNROLL][VPL];
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u) {
+                        const float4 *xr = Xl + (long long)c[u] * k4;
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) x[u][i] = __ldg(xr + i * G);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
+                }
+            }
+            // tail (and the general case): predicated batches of TAIL
+            for (; p < e; p += TAIL) {
+                int c[TAIL];
+                float v[TAIL];
+#pragma unroll
+                for (int u = 0; u < TAIL; ++u) {
                     const bool ok = p + u < e;
                     c[u] = ok ? s_idx[p + u] : -1;
                     v[u] = ok ? s_val[p + u] : 0.f;
                 }
-                float4 x[UNROLL][VPL];
+                float4 x[TAIL][VPL];
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
+                for (int u = 0; u < TAIL; ++u) {
                     const float4 *xr = Xl + (long long)c[u] * k4;
 #pragma unroll
                     for (int i = 0; i < VPL; ++i)
                         x[u][i] = (c[u] >= 0 && gl + i * G < k4) ? __ldg(xr + i * G) : f4_zero();
                 }
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
+                for (int u = 0; u < TAIL; ++u)
 #pragma unroll
                     for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
             }
@@ -635,6 +672,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
             }
         }
         __syncthreads();            // stage `st` may be refilled by the next iteration's prefetch
+        tile = s_next[st];
     }
 }
 
@@ -1045,6 +1083,7 @@ void arrow_ctx_destroy(arrow_ctx *ctx) {
     if (ctx->long_scratch) cudaFree(ctx->long_scratch);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->dev_status) cudaFree(ctx->dev_status);
+    if (ctx->tile_ticket) cudaFree(ctx->tile_ticket);
     for (int l = 1; l < ARROW_N_LANES; ++l)
         if (ctx->lanes[l]) { cudaStreamSynchronize(ctx->lanes[l]); cudaStreamDestroy(ctx->lanes[l]); }
     for (int l = 0; l < ARROW_N_LANES; ++l)
@@ -1560,11 +1599,14 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
         ctx->launches++;
     } else if (variant == 3) {
         if (A->n_tiles > 0) {
+            if (!ctx->tile_ticket) CUDA_TRY(ctx, cudaMalloc(&ctx->tile_ticket, sizeof(int)));
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->tile_ticket, 0, sizeof(int), ctx->stream));
             TileArgs t;
             t.a = a;
             t.tiles = A->tiles;
             t.n_tiles = A->n_tiles;
             t.skip = A->may_skip ? 1 : 0;
+            t.ticket = ctx->tile_ticket;
             int rc = launch_tiles(ctx, t, rm != nullptr, acc, vpl_req);
             if (rc != ARROW_OK) return rc;
         }

@@ -123,6 +123,37 @@ class ShardPlan:
     def own_bounds(self, level: int) -> np.ndarray:
         return self.levels[level].bounds
 
+    def a2a_tables(self, dst_level: int, forward: bool):
+        """Pack / unpack tables of one level exchange for an all-to-all-v (the NCCL backend).
+
+        forward: destination = level ``dst_level`` rows, source = level ``dst_level-1`` (``to_prev``);
+        backward: destination = level ``dst_level`` rows, source = level ``dst_level+1`` (``to_next``).
+        Returns ``pack`` (own source rows in send order), ``send_counts``/``recv_counts`` (rows per peer) and
+        ``unpack`` (own destination row -> position in the receive buffer, -1 if not routed).  Same content as
+        the reference's ``_all_to_all_tables`` (arrow_dec_mpi.py:325-384), built from the global maps."""
+        w = self.width
+        src_level = dst_level - 1 if forward else dst_level + 1
+        dmap = (self.to_prev[dst_level] if forward else self.to_next[dst_level])[: self.levels[dst_level].rows_global]
+        db, sb = self.levels[dst_level].bounds, self.levels[src_level].bounds
+        src_rows = self.levels[src_level].rows_global
+        dst = np.flatnonzero(dmap < src_rows)                         # routed destination rows (global), ascending
+        src = dmap[dst]
+        d_rank = np.searchsorted(db, dst, side="right") - 1
+        s_rank = np.searchsorted(sb, src, side="right") - 1
+        me = self.rank
+        # what I send: my source rows, ordered by (destination rank, destination row)
+        mine = np.flatnonzero(s_rank == me)
+        order = mine[np.lexsort((dst[mine], d_rank[mine]))]
+        pack = src[order] - sb[me]
+        send_counts = np.bincount(d_rank[order], minlength=self.world).astype(np.int64)
+        # what I receive: my destination rows, ordered by (source rank, destination row)
+        tome = np.flatnonzero(d_rank == me)
+        rorder = tome[np.lexsort((dst[tome], s_rank[tome]))]
+        recv_counts = np.bincount(s_rank[rorder], minlength=self.world).astype(np.int64)
+        unpack = np.full(self.levels[dst_level].own_rows, -1, dtype=np.int64)
+        unpack[dst[rorder] - db[me]] = np.arange(rorder.size, dtype=np.int64)
+        return dict(pack=pack.astype(np.int64), send_counts=send_counts, recv_counts=recv_counts, unpack=unpack)
+
 
 # ------------------------------------------------------------------------------------------------------
 # engine
@@ -133,7 +164,7 @@ class ShardedArrowEngine:
     def __init__(self, plan: ShardPlan, k: int, backend):
         self.plan, self.k, self.be = plan, int(k), backend
         self.rank, self.world, self.width, self.L = plan.rank, plan.world, plan.width, plan.L
-        self.mode = "exchange-p2p"
+        self.mode = "exchange-" + type(backend).__name__
         be = backend
         self.mats, self.fwd, self.bwd = [], [], []
         for sh in plan.levels:
@@ -177,17 +208,14 @@ class ShardedArrowEngine:
         be.barrier()                                            # every rank's level-0 features are in place
         for j in range(1, self.L):
             sh, prev = pl.levels[j], pl.levels[j - 1]
-            if sh.own_rows > 0:
-                # C_i[perm] = recvbuf (arrow_dec_mpi.py:544): pull each routed row from the GPU that owns it
-                be.pull_rows(dst=(j, self.ci[j]), dst_off=sh.hoff, src=(j - 1, self.xi[j - 1]), src_bounds=prev.bounds,
-                             row_map=self.fwd[j], accumulate=False)
+            # C_i[perm] = recvbuf (arrow_dec_mpi.py:544): each routed row comes from the GPU that owns it
+            be.pull_rows(dst=(j, self.ci[j]), dst_off=sh.hoff, src=(j - 1, self.xi[j - 1]), src_bounds=prev.bounds,
+                         row_map=self.fwd[j], accumulate=False, forward=True)
             self.xi[j] = self.ci[j]                             # set_features(C_i) (:545)
             be.barrier()
-        # X_0 broadcast of every level (arrow_slim_mpi.py:273): copy GPU 0's head tile
-        if self.rank > 0:
-            for j in range(self.L):
-                hr = min(self.width, pl.levels[j].rows_global)
-                be.copy_from_peer(dst=(j, self.xi[j]), dst_off=0, peer=0, src=(j, self.xi[j]), src_off=0, rows=hr)
+        # X_0 broadcast of every level (arrow_slim_mpi.py:273)
+        for j in range(self.L):
+            be.bcast_head((j, self.xi[j]), min(self.width, pl.levels[j].rows_global))
 
     def spmm(self):
         for j in range(self.L):
@@ -199,19 +227,15 @@ class ShardedArrowEngine:
     def aggregate(self):
         be, pl = self.be, self.plan
         be.barrier()                                            # all partial head tiles are written
-        if self.rank == 0:
-            # C_0 = sum_i A_0i X_i (Reduce to rank 0, arrow_slim_mpi.py:116): add the peers' partial head tiles
-            for j in range(self.L):
-                hr = min(self.width, pl.levels[j].rows_global)
-                for g in range(1, self.world):
-                    be.add_from_peer(dst=(j, self.ci[j]), peer=g, src=(j, self.ci[j]), rows=hr)
+        # C_0 = sum_i A_0i X_i (Reduce to rank 0, arrow_slim_mpi.py:116)
+        for j in range(self.L):
+            be.reduce_head((j, self.ci[j]), min(self.width, pl.levels[j].rows_global))
         be.barrier()
         for j in range(self.L - 1, 0, -1):
             prev, sh = pl.levels[j - 1], pl.levels[j]
-            if prev.own_rows > 0:
-                # C_{j-1}[to_prev[r]] += C_j[r] as a gather-add over this rank's level j-1 rows (:437)
-                be.pull_rows(dst=(j - 1, self.ci[j - 1]), dst_off=prev.hoff, src=(j, self.ci[j]), src_bounds=sh.bounds,
-                             row_map=self.bwd[j - 1], accumulate=True)
+            # C_{j-1}[to_prev[r]] += C_j[r] as a gather-add over this rank's level j-1 rows (:437)
+            be.pull_rows(dst=(j - 1, self.ci[j - 1]), dst_off=prev.hoff, src=(j, self.ci[j]), src_bounds=sh.bounds,
+                         row_map=self.bwd[j - 1], accumulate=True, forward=False)
             self.xi[j - 1] = self.ci[j - 1]                     # set_features(C_i) (:438)
             if j > 1:
                 be.barrier()
@@ -321,9 +345,11 @@ class CudaPeerBackend:
     def spmm(self, A, X, C):
         self.ctx.spmm(A, X, C)
 
-    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate):
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True):
         lvl, which = dst
         n = row_map.n
+        if n == 0:
+            return
         d = self._view(self.rank, lvl, which, dst_off, n)
         srcs = []
         for g in range(self.world):
@@ -335,28 +361,122 @@ class CudaPeerBackend:
     def _hoff(self, g: int) -> int:
         return self.width if g > 0 else 0
 
-    def copy_from_peer(self, dst, dst_off, peer, src, src_off, rows):
-        d = self._view(self.rank, dst[0], dst[1], dst_off, rows)
-        s = self._view(peer, src[0], src[1], src_off, rows)
+    def bcast_head(self, tile, rows):
+        """Every GPU > 0 copies GPU 0's head tile (peer read over NVLink)."""
+        if self.rank == 0:
+            return
+        d = self._view(self.rank, tile[0], tile[1], 0, rows)
+        s = self._view(0, tile[0], tile[1], 0, rows)
         d.copy_from(s, rows=rows)
 
-    def add_from_peer(self, dst, peer, src, rows):
-        d = self._view(self.rank, dst[0], dst[1], 0, rows)
-        s = self._view(peer, src[0], src[1], 0, rows)
+    def reduce_head(self, tile, rows):
+        """GPU 0 pulls the partial head tiles of its peers and adds them (rank order => deterministic)."""
+        if self.rank != 0:
+            return
+        d = self._view(0, tile[0], tile[1], 0, rows)
         ident = self._ident.get(rows)
         if ident is None:
             ident = self.ctx.map_upload(np.arange(rows, dtype=np.int64), rows)
             self._ident[rows] = ident
-        self.ctx.gather_rows(d, s, ident, accumulate=True)
+        for g in range(1, self.world):
+            self.ctx.gather_rows(d, self._view(g, tile[0], tile[1], 0, rows), ident, accumulate=True)
+
+
+class _CudaArray:
+    """``__cuda_array_interface__`` view of a library-owned tile so torch.distributed can address it."""
+
+    def __init__(self, ptr: int, rows: int, k: int):
+        self.__cuda_array_interface__ = {"shape": (rows, k), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class NcclBackend(CudaPeerBackend):
+    """Same engine, but every cross-GPU step is an NCCL collective issued through torch.distributed:
+    level exchange = pack kernel -> ``all_to_all_single`` -> unpack kernel, head tiles = ``broadcast`` / ``reduce``.
+    This is the B200 version of the reference's own scheme (Alltoallv / Bcast / Reduce on host buffers,
+    arrow_dec_mpi.py:442-505, arrow_slim_mpi.py:116, 273) and the A/B baseline for the peer-pull backend."""
+
+    def __init__(self, comm, device: int, width: int, plan: ShardPlan):
+        import torch
+        self.torch = torch
+        super().__init__(comm, device, width, stream=torch.cuda.current_stream().cuda_stream)
+        self.plan = plan
+        self._tables = {}
+        self._bufs = {}
+
+    def alloc_shared_tiles(self, rows_per_level, k):
+        self.k = k
+        self._tiles = [[self.ctx.dense_alloc(r, k), self.ctx.dense_alloc(r, k)] for r in rows_per_level]
+        self._peer = [None] * self.world
+        self._peer[self.rank] = self._tiles
+        self._views = {}
+        return self._tiles
+
+    def barrier(self):
+        pass                                            # collectives carry the ordering
+
+    def _tensor(self, dense, rows):
+        return self.torch.as_tensor(_CudaArray(dense.device_ptr(), rows, self.k), device="cuda")
+
+    def _table(self, dst_level, forward):
+        key = (dst_level, forward)
+        t = self._tables.get(key)
+        if t is None:
+            raw = self.plan.a2a_tables(dst_level, forward)
+            n_send, n_recv = int(raw["send_counts"].sum()), int(raw["recv_counts"].sum())
+            src_level = dst_level - 1 if forward else dst_level + 1
+            t = dict(send_counts=[int(c) for c in raw["send_counts"]], recv_counts=[int(c) for c in raw["recv_counts"]],
+                     n_send=n_send, n_recv=n_recv,
+                     pack=self.ctx.map_upload(raw["pack"], max(self.plan.levels[src_level].own_rows, 1)),
+                     unpack=self.ctx.map_upload(raw["unpack"], max(n_recv, 1)),
+                     sendbuf=self.ctx.dense_alloc(max(n_send, 1), self.k), recvbuf=self.ctx.dense_alloc(max(n_recv, 1), self.k))
+            self._tables[key] = t
+        return t
+
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True):
+        import torch.distributed as dist
+        t = self._table(dst[0], forward)
+        src_sh = self.plan.levels[src[0]]
+        if t["n_send"] > 0:
+            s_own = self._view(self.rank, src[0], src[1], src_sh.hoff, src_sh.own_rows)
+            self.ctx.gather_rows(self._sub(t["sendbuf"], t["n_send"]), s_own, t["pack"])          # pack
+        send_t = self._tensor(t["sendbuf"], t["n_send"])
+        recv_t = self._tensor(t["recvbuf"], t["n_recv"])
+        dist.all_to_all_single(recv_t, send_t, output_split_sizes=t["recv_counts"], input_split_sizes=t["send_counts"])
+        n = row_map.n
+        if n > 0 and t["n_recv"] > 0:
+            d = self._view(self.rank, dst[0], dst[1], dst_off, n)
+            self.ctx.gather_rows(d, self._sub(t["recvbuf"], t["n_recv"]), t["unpack"], accumulate=accumulate)   # unpack
+
+    def _sub(self, dense, rows):
+        key = ("sub", dense.h, rows)
+        v = self._views.get(key)
+        if v is None:
+            v = self.ctx.dense_wrap(dense.device_ptr(), rows, self.k)
+            self._views[key] = v
+        return v
+
+    def bcast_head(self, tile, rows):
+        import torch.distributed as dist
+        dist.broadcast(self._tensor(self._tiles[tile[0]][tile[1]], rows), src=0)
+
+    def reduce_head(self, tile, rows):
+        import torch.distributed as dist
+        dist.reduce(self._tensor(self._tiles[tile[0]][tile[1]], rows), dst=0, op=dist.ReduceOp.SUM)
 
 
 class ShardedArrowDecomposition:
     """Convenience wrapper used by bench.py at N > 1: plan + CUDA peer backend + the reference-like calls."""
 
-    def __init__(self, comm, decomposition, width: int, k: int, device: int = 0):
+    def __init__(self, comm, decomposition, width: int, k: int, device: int = 0, exchange: str = "p2p"):
         self.comm = comm
         plan = ShardPlan(decomposition, width, comm.Get_rank(), comm.Get_size())
-        be = CudaPeerBackend(comm, device, width)
+        if exchange == "p2p":
+            be = CudaPeerBackend(comm, device, width)
+        elif exchange == "nccl":
+            be = NcclBackend(comm, device, width, plan)
+        else:
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.engine = ShardedArrowEngine(plan, k, be)
         self.B = self
         self.matrix_index = 0

@@ -60,7 +60,7 @@ class GlooNumpyBackend:
     def _tile(self, g, level, which):
         return self.tiles[level][which] if g == self.rank else self.snap[g][level][which]
 
-    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate):
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True):
         d = self.tiles[dst[0]][dst[1]]
         m = row_map.m
         for g in range(self.world):
@@ -74,8 +74,11 @@ class GlooNumpyBackend:
             else:
                 d[dst_off + sel] = rows
 
-    def copy_from_peer(self, dst, dst_off, peer, src, src_off, rows):
-        self.tiles[dst[0]][dst[1]][dst_off:dst_off + rows] = self._tile(peer, src[0], src[1])[src_off:src_off + rows]
+    def bcast_head(self, tile, rows):
+        if self.rank > 0:
+            self.tiles[tile[0]][tile[1]][:rows] = self._tile(0, tile[0], tile[1])[:rows]
 
-    def add_from_peer(self, dst, peer, src, rows):
-        self.tiles[dst[0]][dst[1]][:rows] += self._tile(peer, src[0], src[1])[:rows]
+    def reduce_head(self, tile, rows):
+        if self.rank == 0:
+            for g in range(1, self.world):
+                self.tiles[tile[0]][tile[1]][:rows] += self._tile(g, tile[0], tile[1])[:rows]
