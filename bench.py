@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--levels", type=int, default=2)
     ap.add_argument("--perm", type=str, default="random", choices=["random", "local", "identity"])
     ap.add_argument("--mode", type=str, default="auto", choices=["auto", "fused", "exchange"])
+    ap.add_argument("--exchange", type=str, default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU level exchange: NVLink peer pulls (default) or NCCL all-to-all")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-blocks", type=int, default=0)
@@ -178,7 +180,7 @@ def run_b200(a):
     comm = comm_mod.world_comm()
     if world > 1:
         from arrow_matrix_b200.sharded import ShardedArrowDecomposition
-        arrow = ShardedArrowDecomposition(comm, dec, a.width, a.k, device=local_rank)
+        arrow = ShardedArrowDecomposition(comm, dec, a.width, a.k, device=local_rank, exchange=a.exchange)
         eng = arrow.engine
     else:
         # the public path: files on disk -> load_decomposition_new -> initialize -> load blocks

@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, q):
+def _worker(rank, world, port, case, exchange, q):
     try:
         sys.path.insert(0, ROOT)
         import torch
@@ -41,7 +41,7 @@ def _worker(rank, world, port, case, q):
         w, t0, k, levels, nested = {"L2k128": (128, 9, 128, 2, True), "L3k16": (64, 11, 16, 3, True),
                                     "L3stale_k6": (32, 6, 6, 3, False)}[case]
         dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600)
-        arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank)
+        arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank, exchange=exchange)
         eng = arrow.engine
         po = oracle.ReferenceProtocolOracle(dec, w, k)
         rng = np.random.default_rng(2)
@@ -71,14 +71,15 @@ def _worker(rank, world, port, case, q):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6"])
-def test_sharded_engine_on_gpus(case):
+def test_sharded_engine_on_gpus(case, exchange):
     import torch.multiprocessing as mp
     world = min(_n_gpus(), 4)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, exchange, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=300) for _ in procs]
