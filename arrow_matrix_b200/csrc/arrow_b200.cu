@@ -381,6 +381,50 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// ---- L2 eviction policies (createpolicy + .L2::cache_hint) ---------------------------------------------
+// The X rows are the only data with reuse (each row of a block's panel is hit ~nnz/row times from L2);
+// CSR streams and the C tile are touched once.  Marking the gathers evict_last and everything else
+// evict_first keeps the streams from pushing the panels out of L2 (fused level > 0: DRAM traffic was
+// 13.9 GB vs 8.1 GB algorithmic before the hints).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4 *ptr, uint64_t pol) {
+    float4 r;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(ptr), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ld_f4_hint(const float4 *ptr, uint64_t pol) {      // coherent load (C tile RMW)
+    float4 r;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(ptr), "l"(pol)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_f4_hint(float4 *ptr, const float4 &v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                              uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+
 constexpr int TMA_WARPS = 8;      // warps per CTA
 constexpr int TMA_SLOTS = 16;     // X rows staged per stage per warp
 constexpr int TMA_STAGES = 2;
@@ -549,6 +593,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
     const int k4 = a.k4;
     const float4 *__restrict__ Xl = reinterpret_cast<const float4 *>(a.X) + gl;
     float4 *__restrict__ Cl = reinterpret_cast<float4 *>(a.C) + gl;
+    const uint64_t pol_keep = l2_policy_evict_last();
+    const uint64_t pol_stream = l2_policy_evict_first();
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -565,10 +611,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
         const uint32_t nnz_bytes = (uint32_t)(((d.w - a0) + 3) & ~3) * 4u;
         int *sp = stage_base + (size_t)st * TILE_STAGE_WORDS;
         mbar_expect_tx(&bars[st], ptr_bytes + 2u * nnz_bytes);
-        bulk_g2s(sp, a.indptr + rb4, ptr_bytes, &bars[st]);
+        bulk_g2s_hint(sp, a.indptr + rb4, ptr_bytes, &bars[st], pol_stream);
         if (nnz_bytes) {
-            bulk_g2s(sp + TILE_PTR_WORDS, a.indices + a0, nnz_bytes, &bars[st]);
-            bulk_g2s(sp + TILE_PTR_WORDS + TILE_NNZ_WORDS, a.vals + a0, nnz_bytes, &bars[st]);
+            bulk_g2s_hint(sp + TILE_PTR_WORDS, a.indices + a0, nnz_bytes, &bars[st], pol_stream);
+            bulk_g2s_hint(sp + TILE_PTR_WORDS + TILE_NNZ_WORDS, a.vals + a0, nnz_bytes, &bars[st], pol_stream);
         }
     };
 
@@ -626,7 +672,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
                     for (int u = 0; u < UNROLL; ++u) {
                         const float4 *xr = Xl + (long long)c[u] * k4;
 #pragma unroll
-                        for (int i = 0; i < VPL; ++i) x[u][i] = __ldg(xr + i * G);
+                        for (int i = 0; i < VPL; ++i) x[u][i] = ldg_f4_hint(xr + i * G, pol_keep);
                     }
 #pragma unroll
                     for (int u = 0; u < UNROLL; ++u)
@@ -650,7 +696,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
                     const float4 *xr = Xl + (long long)c[u] * k4;
 #pragma unroll
                     for (int i = 0; i < VPL; ++i)
-                        x[u][i] = (c[u] >= 0 && gl + i * G < k4) ? __ldg(xr + i * G) : f4_zero();
+                        x[u][i] = (c[u] >= 0 && gl + i * G < k4) ? ldg_f4_hint(xr + i * G, pol_keep) : f4_zero();
                 }
 #pragma unroll
                 for (int u = 0; u < TAIL; ++u)
@@ -662,12 +708,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
             for (int i = 0; i < VPL; ++i) {
                 if (gl + i * G < k4) {
                     if (ACC) {
-                        float4 old = cr[i * G];
+                        float4 old = ld_f4_hint(cr + i * G, pol_stream);
                         f4_add(acc[i], old);
-                        cr[i * G] = acc[i];
-                    } else {
-                        __stcs(cr + i * G, acc[i]);
                     }
+                    st_f4_hint(cr + i * G, acc[i], pol_stream);
                 }
             }
         }
