@@ -66,7 +66,7 @@ def bench_spmm(path: Optional[str], width: int, n_features: int, iterations: int
         arrow.synchronize()
         comm.Barrier()
         wb_logging.log({"init_time": time.perf_counter() - tic})
-        rows_local = arrow._engine.levels[0].rows
+        rows_local = arrow._engine.local_rows_of(0)
         for i in range(iterations):
             X_p0 = 2 * rng.random((rows_local, n_features), dtype=datatype) - 1      # arrow_bench.py:115
             arrow.B.set_features(X_p0)

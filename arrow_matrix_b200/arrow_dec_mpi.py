@@ -42,7 +42,7 @@ class ArrowDecompositionMPI:
 
     def __init__(self, comm, B: ArrowSlimMPI, matrix_index: int, number_of_rows_per_rank: int,
                  number_of_feature_columns: int, groups, to_previous_permutation, to_next_mapping,
-                 device='gpu', slim=True, block_diagonal=True, n_blocks=None, mode="auto"):
+                 device='gpu', slim=True, block_diagonal=True, n_blocks=None, mode="auto", exchange="p2p"):
         _require_gpu(device)
         self.comm = comm
         self.B = B
@@ -57,14 +57,16 @@ class ArrowDecompositionMPI:
         self._to_prev = to_previous_permutation
         self._to_next = to_next_mapping
         self._mode = mode
-        self._engine: Optional[ArrowEngine] = None
+        self._exchange = exchange
+        self._engine = None
         self.levels: List[ArrowSlimMPI] = [B]
         B._owner = self
 
     # -- factory -----------------------------------------------------------------------------------------
     @staticmethod
     def initialize(comm, n_blocks: np.ndarray, to_prev_permutation, to_next_permutation, rows_per_rank: int,
-                   feature_columns: int, device='gpu', block_diagonal: bool = True, slim: bool = False, mode: str = "auto"):
+                   feature_columns: int, device='gpu', block_diagonal: bool = True, slim: bool = False, mode: str = "auto",
+                   exchange: str = "p2p"):
         """Same arguments as the reference (``:106-115``).  ``slim`` only selects the reference's rank
         layout; on a GPU both layouts are the same row-partitioned kernels, so it is accepted and ignored."""
         assert not slim or block_diagonal
@@ -72,7 +74,7 @@ class ArrowDecompositionMPI:
         B = ArrowSlimMPI(comm)
         arrow = ArrowDecompositionMPI(comm, B, 0, rows_per_rank, feature_columns, None, to_prev_permutation,
                                       to_next_permutation, device=device, slim=slim, block_diagonal=block_diagonal,
-                                      n_blocks=[int(b) for b in n_blocks], mode=mode)
+                                      n_blocks=[int(b) for b in n_blocks], mode=mode, exchange=exchange)
         arrow.levels = [B] + [ArrowSlimMPI(comm, arrow, j) for j in range(1, len(n_blocks))]
         return arrow
 
@@ -83,8 +85,19 @@ class ArrowDecompositionMPI:
             raise ValueError(f"decomposition was loaded for width {blocks.width}, initialised for {self._n_rows_per_rank}")
         if self._engine is not None:
             self._engine.close()
-        self._engine = ArrowEngine(blocks.decomposition, blocks.width, self._n_feature_columns,
-                                   block_diagonal=blocks.block_diagonal, mode=self._mode, n_blocks=self.n_blocks)
+        if self.comm.Get_size() > 1:
+            # one process per GPU: this rank's block-rows of every level, straight from the memory maps
+            import os
+            from .sharded import CudaPeerBackend, NcclBackend, ShardPlan, ShardedArrowEngine
+            dev = int(os.environ.get("LOCAL_RANK", self.comm.Get_rank()))
+            plan = ShardPlan(blocks.decomposition, blocks.width, self.comm.Get_rank(), self.comm.Get_size(),
+                             block_diagonal=blocks.block_diagonal, n_blocks=self.n_blocks)
+            be = NcclBackend(self.comm, dev, blocks.width, plan) if self._exchange == "nccl" \
+                else CudaPeerBackend(self.comm, dev, blocks.width)
+            self._engine = ShardedArrowEngine(plan, self._n_feature_columns, be)
+        else:
+            self._engine = ArrowEngine(blocks.decomposition, blocks.width, self._n_feature_columns,
+                                       block_diagonal=blocks.block_diagonal, mode=self._mode, n_blocks=self.n_blocks)
         self.decomposition_length = self._engine.L
 
     def load_data_from_blocks(self, blocked: DecompositionBlocks):
@@ -101,8 +114,7 @@ class ArrowDecompositionMPI:
 
     def _propagate_features(self):
         eng = self._require_engine()
-        if eng.mode != "exchange":
-            self._to_exchange_mode()
+        eng.ensure_level_tiles()
         tic = time.perf_counter()
         eng.propagate_features()
         wb_logging.log({"spmm_bcast_time": time.perf_counter() - tic})
@@ -117,29 +129,16 @@ class ArrowDecompositionMPI:
     def step_stream(self, X_host: np.ndarray, out_host: np.ndarray):
         """Extension for host-resident features: enqueue ``set_features(X); step(); result_tile(out)`` so that
         uploads, compute and downloads of consecutive iterations overlap (see ``ArrowEngine.stream_step``).
-        Call ``synchronize()`` before reading ``out_host``."""
-        self._require_engine().stream_step(X_host, out_host)
+        Call ``synchronize()`` before reading ``out_host``.  Single-GPU engine only."""
+        eng = self._require_engine()
+        if not hasattr(eng, "stream_step"):
+            raise NotImplementedError("step_stream is implemented for the single-GPU engine")
+        eng.stream_step(X_host, out_host)
 
     def synchronize(self):
-        eng = self._require_engine()
-        if hasattr(eng, "_slots"):
-            eng.stream_drain()
-        eng.ctx.sync()
+        self._require_engine().sync()
 
-    def _to_exchange_mode(self):
-        """Materialise per-level tiles (needed to observe levels > 0): re-runs nothing, keeps level-0 tiles."""
-        eng = self._engine
-        st0 = eng.levels[0]
-        keep = [b.d2h() for b in st0.bufs]
-        xi, ci = st0.xi, st0.ci
-        eng.set_mode("exchange")
-        st0 = eng.levels[0]
-        for b, h in zip(st0.bufs, keep):
-            b.h2d(h)
-        st0.xi, st0.ci = xi, ci
-        eng.ctx.sync()
-
-    def _require_engine(self) -> ArrowEngine:
+    def _require_engine(self):
         if self._engine is None:
             raise RuntimeError("sparse blocks not loaded yet: call B.load_sparse_matrix_from_blocks(blocks)")
         return self._engine

@@ -37,16 +37,10 @@ class ArrowSlimMPI(ArrowMatrix):
     def spmm(self, device: str = 'gpu'):
         """This level's arrow product on its current features (``_arrow_spmm``, arrow_slim_mpi.py:246-280)."""
         _require_gpu(device)
-        eng = self._engine
-        if eng.mode != "exchange":
-            eng.set_mode("exchange")
-        st = eng.levels[self._level]
-        out = 1 - st.xi
-        eng.ctx.spmm(st.csr, st.bufs[st.xi], st.bufs[out], variant=eng.variant)
-        st.ci = out
+        self._engine.spmm_level(self._level)
 
     def result_tile(self, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """Host copy of the result rows; pass a (pinned) ``out`` array to avoid an allocation per call."""
+        """Host copy of this process's result rows; pass a (pinned) ``out`` array to avoid an allocation per call."""
         return self._engine.result(self._level, out)
 
     @property
@@ -55,11 +49,7 @@ class ArrowSlimMPI(ArrowMatrix):
         return self.result_tile()
 
     def feature_tile(self) -> np.ndarray:
-        eng = self._engine
-        st = eng.levels[self._level]
-        if st.bufs[st.xi] is None:
-            raise RuntimeError("level tiles are not materialised in fused mode")
-        return st.bufs[st.xi].d2h()
+        return self._engine.features(self._level)
 
     def set_features(self, X: np.ndarray) -> None:
         """Upload this process's feature rows (level 0).  The reference keeps a reference to ``X``
@@ -81,26 +71,28 @@ class ArrowSlimMPI(ArrowMatrix):
         eng = self._engine
         if number_of_columns != eng.k or number_of_rows_per_rank != eng.width:
             raise ValueError(f"engine was initialised for width={eng.width}, k={eng.k}")
-        for st in eng.levels:
-            for b in st.bufs:
-                if b is not None:
-                    b.fill(0.0)
-            st.xi = st.ci = 0
+        eng.zero_rhs()
 
     def is_column_rank(self) -> bool:
         return True
 
     def allgather_result(self, C: np.ndarray) -> np.ndarray:
+        """Fill the caller's ``(tiles_per_side*width) x k`` array with the whole level's result (every process)."""
         assert C is not None
         eng = self._engine
-        rows = eng.levels[self._level].rows
-        if C.shape != (rows, eng.k) or C.dtype != np.float32:
-            raise ValueError(f"C must be float32 of shape {(rows, eng.k)}")
-        C[:] = eng.result(self._level)
+        mine = eng.result(self._level)
+        parts = self.comm.allgather(mine) if self.comm.Get_size() > 1 else [mine]
+        full = np.concatenate(parts) if len(parts) > 1 else parts[0]
+        if C.shape != full.shape or C.dtype != np.float32:
+            raise ValueError(f"C must be float32 of shape {full.shape}")
+        C[:] = full
         return C
 
     def set_features_slice_from_features(self, X: np.ndarray) -> None:
-        self.set_features(X[: self._engine.levels[0].rows])
+        """Take this process's rows out of the full level-0 feature matrix."""
+        eng = self._engine
+        r0 = eng.plan.levels[0].r0 if hasattr(eng, "plan") else 0
+        self.set_features(X[r0:r0 + eng.local_rows_of(0)])
 
     @staticmethod
     def column_subgroup(tiles_per_side, group):

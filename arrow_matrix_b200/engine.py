@@ -161,6 +161,52 @@ class ArrowEngine:
     def result(self, level: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
         return self.result_buffer(level).d2h(out)
 
+    # -- small uniform API shared with the sharded engine (used by the reference-facing classes) ----------
+    def local_rows_of(self, level: int) -> int:
+        return self.levels[level].rows
+
+    def zero_rhs(self):
+        """``zero_rhs`` on every rank of every level (arrow_slim_mpi.py:354-394)."""
+        for st in self.levels:
+            for b in st.bufs:
+                if b is not None:
+                    b.fill(0.0)
+            st.xi = st.ci = 0
+
+    def features(self, level: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        st = self.levels[level]
+        if st.bufs[st.xi] is None:
+            raise RuntimeError("level tiles are not materialised in fused mode; use mode='exchange'")
+        return st.bufs[st.xi].d2h(out)
+
+    def spmm_level(self, level: int):
+        """One level's arrow product on its current features (``B.spmm()`` of that level)."""
+        if self.mode != "exchange":
+            self.set_mode("exchange")
+        st = self.levels[level]
+        out = 1 - st.xi
+        self.ctx.spmm(st.csr, st.bufs[st.xi], st.bufs[out], variant=self.variant)
+        st.ci = out
+
+    def ensure_level_tiles(self):
+        """Materialise per-level tiles (exchange mode) keeping level 0's current tiles."""
+        if self.mode == "exchange":
+            return
+        st0 = self.levels[0]
+        keep = [b.d2h() for b in st0.bufs]
+        xi, ci = st0.xi, st0.ci
+        self.set_mode("exchange")
+        st0 = self.levels[0]
+        for b, h in zip(st0.bufs, keep):
+            b.h2d(h)
+        st0.xi, st0.ci = xi, ci
+        self.ctx.sync()
+
+    def sync(self):
+        if hasattr(self, "_slots"):
+            self.stream_drain()
+        self.ctx.sync()
+
     # -- the iteration ----------------------------------------------------------------------------------
     def propagate_features(self):
         """Forward exchange (``_propagate_features_forwards``, arrow_dec_mpi.py:507-550)."""

@@ -202,6 +202,50 @@ class ShardedArrowEngine:
         sh = self.plan.levels[level]
         return self.be.d2h(self.tiles[level][self.ci[level]], sh.hoff, sh.own_rows, out)
 
+    # -- small uniform API shared with the single-GPU engine ---------------------------------------------------
+    @property
+    def n_blocks(self):
+        return self.plan.n_blocks
+
+    def local_rows_of(self, level: int) -> int:
+        return self.plan.levels[level].own_rows
+
+    def zero_rhs(self):
+        for pair in self.tiles:
+            for t in pair:
+                self.be.fill(t, 0.0)
+        self.xi = [0] * self.L
+        self.ci = [0] * self.L
+
+    def features(self, level: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        sh = self.plan.levels[level]
+        return self.be.d2h(self.tiles[level][self.xi[level]], sh.hoff, sh.own_rows, out)
+
+    def spmm_level(self, level: int):
+        """One level's distributed arrow product (X_0 broadcast, local SpMM, C_0 reduce): ``B.spmm()``."""
+        be, sh = self.be, self.plan.levels[level]
+        hr = min(self.width, sh.rows_global)
+        be.barrier()
+        be.bcast_head((level, self.xi[level]), hr)
+        out = 1 - self.xi[level]
+        if self.mats[level] is not None and sh.local_rows > 0:
+            be.spmm(self.mats[level], self.tiles[level][self.xi[level]], self.tiles[level][out])
+        self.ci[level] = out
+        be.barrier()
+        be.reduce_head((level, out), hr)
+        be.barrier()
+
+    def ensure_level_tiles(self):
+        pass                                                    # the sharded engine always materialises them
+
+    def sync(self):
+        self.be.sync()
+
+    def close(self):
+        if getattr(self.be, "ctx", None) is not None:
+            self.be.sync()
+            self.be.ctx.close()
+
     # -- the iteration -----------------------------------------------------------------------------------------
     def propagate_features(self):
         be, pl = self.be, self.plan
@@ -328,6 +372,9 @@ class CudaPeerBackend:
 
     def h2d(self, tile, off, X):
         tile.h2d(X, row0=off)
+
+    def fill(self, tile, v):
+        tile.fill(v)
 
     def d2h(self, tile, off, rows, out=None):
         return tile.d2h(out, row0=off, rows=rows)

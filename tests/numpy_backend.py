@@ -47,6 +47,9 @@ class GlooNumpyBackend:
     def sync(self):
         pass
 
+    def fill(self, tile, v):
+        tile[:] = v
+
     def barrier(self):
         self.snap = self.comm.allgather([[t.copy() for t in pair] for pair in self.tiles])
         self.n_barriers += 1
