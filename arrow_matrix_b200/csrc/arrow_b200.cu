@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -658,27 +659,34 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
             for (int i = 0; i < VPL; ++i) acc[i] = f4_zero();
             int p = s;
             if (EXACT && !t.skip) {
-                // full batches: no bounds / validity predicates at all (the common case)
-                for (; p + UNROLL <= e; p += UNROLL) {
-                    int c[UNROLL];
-                    float v[UNROLL];
+                // unpredicated batches: full UNROLL batches, then the remainder as 4 / 2 / 1 (binary decomposition) --
+                // a predicated tail batch costs as many instructions as a full one
+                auto batch = [&](auto n_tag) {
+                    constexpr int N = decltype(n_tag)::value;
+                    int c[N];
+                    float v[N];
 #pragma unroll
-                    for (int u = 0; u < UNROLL; ++u) {
+                    for (int u = 0; u < N; ++u) {
                         c[u] = s_idx[p + u];
                         v[u] = s_val[p + u];
                     }
-                    float4 x[UNROLL][VPL];
+                    float4 x[N][VPL];
 #pragma unroll
-                    for (int u = 0; u < UNROLL; ++u) {
+                    for (int u = 0; u < N; ++u) {
                         const float4 *xr = Xl + (long long)c[u] * k4;
 #pragma unroll
                         for (int i = 0; i < VPL; ++i) x[u][i] = ldg_f4_hint(xr + i * G, pol_keep);
                     }
 #pragma unroll
-                    for (int u = 0; u < UNROLL; ++u)
+                    for (int u = 0; u < N; ++u)
 #pragma unroll
                         for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
-                }
+                    p += N;
+                };
+                while (p + UNROLL <= e) batch(std::integral_constant<int, UNROLL>{});
+                if constexpr (UNROLL >= 8) { if (e - p >= 4) batch(std::integral_constant<int, 4>{}); }
+                if constexpr (UNROLL >= 4) { if (e - p >= 2) batch(std::integral_constant<int, 2>{}); }
+                if (e - p >= 1) batch(std::integral_constant<int, 1>{});
             }
             // tail (and the general case): predicated batches of TAIL
             for (; p < e; p += TAIL) {
