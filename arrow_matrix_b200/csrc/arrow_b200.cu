@@ -406,10 +406,9 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float4 *ptr, uint64_t pol) {
 }
 __device__ __forceinline__ float4 ld_f4_hint(const float4 *ptr, uint64_t pol) {      // coherent load (C tile RMW)
     float4 r;
-    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(ptr), "l"(pol)
-                 : "memory");
+    asm("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(ptr), "l"(pol));
     return r;
 }
 __device__ __forceinline__ void st_f4_hint(float4 *ptr, const float4 &v, uint64_t pol) {
@@ -654,9 +653,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
                 orow = __ldg(a.rowmap + row);
                 if (orow < 0) continue;
             }
+            // accumulate mode: the old C row is read FIRST so that its latency hides behind the gathers (only this
+            // group ever touches the row: the row maps are injective)
             float4 acc[VPL];
+            float4 *cr = Cl + orow * k4;
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) acc[i] = f4_zero();
+            for (int i = 0; i < VPL; ++i)
+                acc[i] = (ACC && gl + i * G < k4) ? ld_f4_hint(cr + i * G, pol_stream) : f4_zero();
             int p = s;
             if (EXACT && !t.skip) {
                 // unpredicated batches: full UNROLL batches, then the remainder as 4 / 2 / 1 (binary decomposition) --
@@ -711,17 +714,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
 #pragma unroll
                     for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
             }
-            float4 *cr = Cl + orow * k4;
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) {
-                if (gl + i * G < k4) {
-                    if (ACC) {
-                        float4 old = ld_f4_hint(cr + i * G, pol_stream);
-                        f4_add(acc[i], old);
-                    }
-                    st_f4_hint(cr + i * G, acc[i], pol_stream);
-                }
-            }
+            for (int i = 0; i < VPL; ++i)
+                if (gl + i * G < k4) st_f4_hint(cr + i * G, acc[i], pol_stream);
         }
         __syncthreads();            // stage `st` may be refilled by the next iteration's prefetch
         tile = s_next[st];
@@ -844,36 +839,50 @@ struct MultiSrc {
     int n;
 };
 
-template <typename VT, bool ACC, bool MULTI>
+// A group of G lanes moves one row (VPR vectors of VT); rows are taken warp-strided so that a warp's
+// destination rows are consecutive (coalesced stores) while the sources are wherever the map points --
+// local HBM, or a peer GPU's memory over NVLink when MULTI.
+template <typename VT, int G, bool ACC, bool MULTI>
 __global__ void __launch_bounds__(256) k_gather_rows(VT *__restrict__ dst, const VT *__restrict__ src, MultiSrc ms,
                                                      const int *__restrict__ map, long long n_rows, int vec_per_row) {
-    const long long total = n_rows * vec_per_row;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
-        const long long r = t / vec_per_row;
-        const int v = (int)(t - r * vec_per_row);
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G, gi = lane / G;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (long long r = warp_id * RPW + gi; r < n_rows; r += warps_total * RPW) {
         const int m = __ldg(map + r);
         if (m < 0) continue;
-        VT val;
+        const VT *sp;
         if (MULTI) {
             int s = 0;
 #pragma unroll 1
             while (s + 1 < ms.n && (long long)m >= ms.bound[s + 1]) ++s;
-            const VT *sp = reinterpret_cast<const VT *>(ms.p[s]);
-            val = sp[((long long)m - ms.bound[s]) * vec_per_row + v];
+            sp = reinterpret_cast<const VT *>(ms.p[s]) + ((long long)m - ms.bound[s]) * vec_per_row;
         } else {
-            val = __ldg(src + (long long)m * vec_per_row + v);
+            sp = src + (long long)m * vec_per_row;
         }
-        VT *d = dst + t;
-        if (ACC) {
-            VT old = *d;
-            if constexpr (sizeof(VT) == 16) {
-                f4_add(val, old);
-            } else {
-                val += old;
+        VT *dp = dst + r * vec_per_row;
+        for (int v0 = gl; v0 < vec_per_row; v0 += 4 * G) {
+            VT val[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (v0 + j * G < vec_per_row) val[j] = sp[v0 + j * G];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (v0 + j * G < vec_per_row) {
+                    if (ACC) {
+                        VT old = dp[v0 + j * G];
+                        if constexpr (sizeof(VT) == 16) {
+                            f4_add(val[j], old);
+                        } else {
+                            val[j] += old;
+                        }
+                    }
+                    dp[v0 + j * G] = val[j];
+                }
             }
         }
-        *d = val;
     }
 }
 
@@ -1717,20 +1726,35 @@ static int gather_common(arrow_ctx *ctx, DenseBuf *D, const float *src, const Mu
     const int k = D->k;
     const bool vec = (k % 4 == 0);
     const int vpr = vec ? k / 4 : k;
-    const long long total = n_rows * vpr;
+    int g = 1;
+    while (g < vpr && g < 32) g <<= 1;                       // lanes per row
+    if (g > 8 && vpr <= 32) g = 8;                           // 8 lanes x 4 vectors cover k <= 128 in one pass
     const int threads = 256;
-    int grid = (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 16);
+    const long long rows_per_cta = (threads / 32) * (32 / g);
+    int grid = (int)std::min<long long>((n_rows + rows_per_cta - 1) / rows_per_cta, (long long)ctx->sm_count * 8);
     grid = std::max(grid, 1);
-#define LAUNCH_GA(VT, ACCV, MULTIV)                                                                              \
-    k_gather_rows<VT, ACCV, MULTIV><<<grid, threads, 0, ctx->stream>>>(reinterpret_cast<VT *>(D->p),            \
-                                                                      reinterpret_cast<const VT *>(src), ms, m->p, n_rows, vpr)
+#define LAUNCH_GA(VT, GG, ACCV, MULTIV)                                                                          \
+    k_gather_rows<VT, GG, ACCV, MULTIV><<<grid, threads, 0, ctx->stream>>>(reinterpret_cast<VT *>(D->p),         \
+                                                                           reinterpret_cast<const VT *>(src), ms, m->p, n_rows, vpr)
+#define DISPATCH_G(VT, ACCV, MULTIV)                                                                             \
+    do {                                                                                                         \
+        switch (g) {                                                                                             \
+            case 1: LAUNCH_GA(VT, 1, ACCV, MULTIV); break;                                                       \
+            case 2: LAUNCH_GA(VT, 2, ACCV, MULTIV); break;                                                       \
+            case 4: LAUNCH_GA(VT, 4, ACCV, MULTIV); break;                                                       \
+            case 8: LAUNCH_GA(VT, 8, ACCV, MULTIV); break;                                                       \
+            case 16: LAUNCH_GA(VT, 16, ACCV, MULTIV); break;                                                     \
+            default: LAUNCH_GA(VT, 32, ACCV, MULTIV); break;                                                     \
+        }                                                                                                        \
+    } while (0)
     if (vec) {
-        if (multi) { if (acc) LAUNCH_GA(float4, true, true); else LAUNCH_GA(float4, false, true); }
-        else       { if (acc) LAUNCH_GA(float4, true, false); else LAUNCH_GA(float4, false, false); }
+        if (multi) { if (acc) DISPATCH_G(float4, true, true); else DISPATCH_G(float4, false, true); }
+        else       { if (acc) DISPATCH_G(float4, true, false); else DISPATCH_G(float4, false, false); }
     } else {
-        if (multi) { if (acc) LAUNCH_GA(float, true, true); else LAUNCH_GA(float, false, true); }
-        else       { if (acc) LAUNCH_GA(float, true, false); else LAUNCH_GA(float, false, false); }
+        if (multi) { if (acc) DISPATCH_G(float, true, true); else DISPATCH_G(float, false, true); }
+        else       { if (acc) DISPATCH_G(float, true, false); else DISPATCH_G(float, false, false); }
     }
+#undef DISPATCH_G
 #undef LAUNCH_GA
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());

@@ -446,7 +446,9 @@ class NcclBackend(CudaPeerBackend):
     def __init__(self, comm, device: int, width: int, plan: ShardPlan):
         import torch
         self.torch = torch
-        super().__init__(comm, device, width, stream=torch.cuda.current_stream().cuda_stream)
+        # run on torch's current stream so kernels and NCCL collectives are ordered; torch's default stream is the
+        # legacy default stream (handle 0), which CUDA also names cudaStreamLegacy = 0x1
+        super().__init__(comm, device, width, stream=torch.cuda.current_stream().cuda_stream or 1)
         self.plan = plan
         self._tables = {}
         self._bufs = {}
