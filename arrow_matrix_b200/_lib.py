@@ -27,7 +27,7 @@ EXPORTS = [
     "arrow_map_upload", "arrow_map_free", "arrow_map_compose", "arrow_map_invert", "arrow_map_d2h",
     "arrow_dense_alloc", "arrow_dense_free", "arrow_dense_fill", "arrow_dense_h2d", "arrow_dense_d2h",
     "arrow_dense_copy", "arrow_dense_ptr", "arrow_dense_wrap", "arrow_host_alloc", "arrow_host_free",
-    "arrow_dense_h2d_lane", "arrow_dense_d2h_lane", "arrow_lane_wait", "arrow_lane_sync",
+    "arrow_dense_h2d_lane", "arrow_dense_d2h_lane", "arrow_lane_wait", "arrow_lane_sync", "arrow_set_lane",
     "arrow_event_record", "arrow_event_wait",
     "arrow_spmm", "arrow_gather_rows", "arrow_gather_rows_multi",
     "arrow_ipc_export", "arrow_ipc_import", "arrow_peer_barrier",
@@ -87,6 +87,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         "arrow_dense_d2h_lane": (c_int, [P, I, I, I64, I64, P]),
         "arrow_lane_wait": (c_int, [P, I, I]),
         "arrow_lane_sync": (c_int, [P, I]),
+        "arrow_set_lane": (c_int, [P, I]),
         "arrow_event_record": (c_int, [P, I, I]),
         "arrow_event_wait": (c_int, [P, I, I]),
         "arrow_host_alloc": (c_int, [c_size_t, POINTER(P)]),
@@ -278,6 +279,9 @@ class Context:
 
     def lane_sync(self, lane: int):
         self._check(self.lib.arrow_lane_sync(self._h, lane))
+
+    def set_lane(self, lane: int):
+        self._check(self.lib.arrow_set_lane(self._h, lane))
 
     def event_record(self, event: int, lane: int):
         self._check(self.lib.arrow_event_record(self._h, event, lane))

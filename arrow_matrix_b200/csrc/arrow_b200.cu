@@ -100,7 +100,8 @@ struct arrow_ctx {
     size_t long_scratch_bytes = 0;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
-    unsigned int barrier_epoch = 0;
+    unsigned int barrier_epoch[3] = {0, 0, 0};   // one epoch counter per lane (each lane has its own flag set)
+    int cur_lane = 0;                             // lane used by gather / barrier / copy launches (arrow_set_lane)
     int *dev_status = nullptr;        // device-side status word (barrier timeout)
     int *tile_ticket = nullptr;       // device counter of the dynamic tile scheduler
     cudaStream_t lanes[ARROW_N_LANES] = {nullptr, nullptr, nullptr};   // lane 0 = main stream
@@ -121,6 +122,10 @@ int fail(arrow_ctx *ctx, int code, const char *fmt, ...) {
     return code;
 }
 
+cudaStream_t cur_stream(arrow_ctx *ctx) {
+    return (ctx->cur_lane > 0 && ctx->lanes[ctx->cur_lane]) ? ctx->lanes[ctx->cur_lane] : ctx->stream;
+}
+
 #define CUDA_TRY(ctx, expr)                                                                   \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
@@ -137,6 +142,8 @@ int fail(arrow_ctx *ctx, int code, const char *fmt, ...) {
             return fail((ctx), ARROW_ERR_CUDA, "cudaSetDevice(%d): %s", (ctx)->device,        \
                         cudaGetErrorString(_e));                                              \
     } while (0)
+
+cudaStream_t cur_stream(arrow_ctx *ctx);
 
 template <class T>
 int new_slot(std::vector<T> &v) {
@@ -1562,7 +1569,7 @@ int arrow_dense_copy(arrow_ctx *ctx, int dst, int64_t dst_row0, int src, int64_t
         return fail(ctx, ARROW_ERR_ARG, "copy range outside tiles");
     if (rows == 0) return ARROW_OK;
     CUDA_TRY(ctx, cudaMemcpyAsync(a->p + (size_t)dst_row0 * a->k, b->p + (size_t)src_row0 * b->k, (size_t)rows * a->k * 4,
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
+                                  cudaMemcpyDeviceToDevice, cur_stream(ctx)));
     return ARROW_OK;
 }
 
@@ -1734,7 +1741,7 @@ static int gather_common(arrow_ctx *ctx, DenseBuf *D, const float *src, const Mu
     int grid = (int)std::min<long long>((n_rows + rows_per_cta - 1) / rows_per_cta, (long long)ctx->sm_count * 8);
     grid = std::max(grid, 1);
 #define LAUNCH_GA(VT, GG, ACCV, MULTIV)                                                                          \
-    k_gather_rows<VT, GG, ACCV, MULTIV><<<grid, threads, 0, ctx->stream>>>(reinterpret_cast<VT *>(D->p),         \
+    k_gather_rows<VT, GG, ACCV, MULTIV><<<grid, threads, 0, cur_stream(ctx)>>>(reinterpret_cast<VT *>(D->p),     \
                                                                            reinterpret_cast<const VT *>(src), ms, m->p, n_rows, vpr)
 #define DISPATCH_G(VT, ACCV, MULTIV)                                                                             \
     do {                                                                                                         \
@@ -1869,14 +1876,25 @@ int arrow_peer_barrier(arrow_ctx *ctx, const int *flag_bufs, int rank, int world
         if (!d || (long long)d->rows * d->k < world) return fail(ctx, ARROW_ERR_HANDLE, "bad flag tile for rank %d", s);
         pf.p[s] = reinterpret_cast<unsigned int *>(d->p);
     }
-    ctx->barrier_epoch++;
-    k_peer_barrier<<<1, 32, 0, ctx->stream>>>(pf, rank, world, ctx->barrier_epoch, ctx->dev_status);
+    ctx->barrier_epoch[ctx->cur_lane]++;
+    k_peer_barrier<<<1, 32, 0, cur_stream(ctx)>>>(pf, rank, world, ctx->barrier_epoch[ctx->cur_lane], ctx->dev_status);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     return ARROW_OK;
 }
 
-// ---- copy lanes: host staging on side streams, ordered against the main stream with events ----------
+// ---- lanes: side streams ordered against the main stream with events ---------------------------------
+static int lane_stream(arrow_ctx *ctx, int lane, cudaStream_t *out);
+
+int arrow_set_lane(arrow_ctx *ctx, int lane) {
+    CHECK_CTX(ctx);
+    cudaStream_t st;
+    int rc = lane_stream(ctx, lane, &st);          // creates the stream on first use
+    if (rc != ARROW_OK) return rc;
+    ctx->cur_lane = lane;
+    return ARROW_OK;
+}
+
 static int lane_stream(arrow_ctx *ctx, int lane, cudaStream_t *out) {
     if (lane < 0 || lane >= ARROW_N_LANES) return fail(ctx, ARROW_ERR_ARG, "lane %d out of range", lane);
     if (lane == ARROW_LANE_MAIN) { *out = ctx->stream; return ARROW_OK; }

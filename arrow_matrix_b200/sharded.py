@@ -161,8 +161,9 @@ class ShardPlan:
 class ShardedArrowEngine:
     """Executes a ShardPlan.  ``backend`` supplies device memory, kernels, peer access and barriers."""
 
-    def __init__(self, plan: ShardPlan, k: int, backend):
+    def __init__(self, plan: ShardPlan, k: int, backend, overlap: bool = False):
         self.plan, self.k, self.be = plan, int(k), backend
+        self.overlap = bool(overlap) and hasattr(backend, "side_begin")
         self.rank, self.world, self.width, self.L = plan.rank, plan.world, plan.width, plan.L
         self.mode = "exchange-" + type(backend).__name__
         be = backend
@@ -284,9 +285,35 @@ class ShardedArrowEngine:
             if j > 1:
                 be.barrier()
 
+    def _spmm_one(self, j: int):
+        out = 1 - self.xi[j]
+        if self.mats[j] is not None and self.plan.levels[j].local_rows > 0:
+            self.be.spmm(self.mats[j], self.tiles[j][self.xi[j]], self.tiles[j][out])
+        self.ci[j] = out
+
     def step(self):
-        self.propagate_features()
-        self.spmm()
+        if not self.overlap:
+            self.propagate_features()
+            self.spmm()
+            self.aggregate()
+            return
+        # overlap: the forward exchange (NVLink pulls + their barriers) runs on a side lane while the main lane
+        # broadcasts level 0's head tile and multiplies level 0 -- both only read level-0 features
+        be, pl = self.be, self.plan
+        be.barrier()
+        be.side_begin()
+        for j in range(1, self.L):
+            sh, prev = pl.levels[j], pl.levels[j - 1]
+            be.pull_rows(dst=(j, self.ci[j]), dst_off=sh.hoff, src=(j - 1, self.xi[j - 1]), src_bounds=prev.bounds,
+                         row_map=self.fwd[j], accumulate=False, forward=True, side=True)
+            self.xi[j] = self.ci[j]
+            be.barrier(side=True)
+        be.bcast_head((0, self.xi[0]), min(self.width, pl.levels[0].rows_global))
+        self._spmm_one(0)
+        be.side_join()
+        for j in range(1, self.L):
+            be.bcast_head((j, self.xi[j]), min(self.width, pl.levels[j].rows_global))
+            self._spmm_one(j)
         self.aggregate()
 
     # -- accounting ----------------------------------------------------------------------------------------------
@@ -336,7 +363,7 @@ class CudaPeerBackend:
         ctx = self.ctx
         self.k = k
         align = 64                                              # floats (256 bytes)
-        offs, pos = [], 64                                      # first 64 floats: barrier flags
+        offs, pos = [], 128                                     # first 128 floats: barrier flags of the two lanes
         for r in rows_per_level:
             pair = []
             for _ in range(2):
@@ -353,6 +380,7 @@ class CudaPeerBackend:
             arena = self._arena if g == self.rank else ctx.ipc_import(info["handle"], info["arena_rows"], 64)
             base = arena.device_ptr()
             self._flags.append(ctx.dense_wrap(base, 1, 64))
+            self._flags_side = getattr(self, "_flags_side", []) + [ctx.dense_wrap(base + 64 * 4, 1, 64)]
             self._peer.append([[ctx.dense_wrap(base + o * 4, r, k) for o in pair] for pair, r in zip(info["offs"], info["rows"])])
             if g != self.rank:
                 self._imported = getattr(self, "_imported", []) + [arena]
@@ -382,9 +410,25 @@ class CudaPeerBackend:
     def sync(self):
         self.ctx.sync()
 
-    def barrier(self):
-        if self.world > 1:
+    SIDE = 1            # lane id of the side stream
+
+    def barrier(self, side: bool = False):
+        if self.world <= 1:
+            return
+        if side:
+            self.ctx.set_lane(self.SIDE)
+            self.ctx.peer_barrier(self._flags_side, self.rank)
+            self.ctx.set_lane(0)
+        else:
             self.ctx.peer_barrier(self._flags, self.rank)
+
+    def side_begin(self):
+        """the side lane waits for everything issued so far on the main lane"""
+        self.ctx.lane_wait(self.SIDE, 0)
+
+    def side_join(self):
+        """the main lane waits for everything issued so far on the side lane"""
+        self.ctx.lane_wait(0, self.SIDE)
 
     def allreduce_sum(self, v):
         return sum(self.comm.allgather(int(v)))
@@ -392,11 +436,22 @@ class CudaPeerBackend:
     def spmm(self, A, X, C):
         self.ctx.spmm(A, X, C)
 
-    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True):
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True, side=False):
         lvl, which = dst
         n = row_map.n
         if n == 0:
             return
+        if side:
+            self.ctx.set_lane(self.SIDE)
+        try:
+            self._pull_rows(dst, dst_off, src, src_bounds, row_map, accumulate)
+        finally:
+            if side:
+                self.ctx.set_lane(0)
+
+    def _pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate):
+        lvl, which = dst
+        n = row_map.n
         d = self._view(self.rank, lvl, which, dst_off, n)
         srcs = []
         for g in range(self.world):
@@ -461,8 +516,14 @@ class NcclBackend(CudaPeerBackend):
         self._views = {}
         return self._tiles
 
-    def barrier(self):
+    def barrier(self, side: bool = False):
         pass                                            # collectives carry the ordering
+
+    def side_begin(self):
+        pass
+
+    def side_join(self):
+        pass
 
     def _tensor(self, dense, rows):
         return self.torch.as_tensor(_CudaArray(dense.device_ptr(), rows, self.k), device="cuda")
@@ -482,7 +543,7 @@ class NcclBackend(CudaPeerBackend):
             self._tables[key] = t
         return t
 
-    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True):
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True, side=False):
         import torch.distributed as dist
         t = self._table(dst[0], forward)
         src_sh = self.plan.levels[src[0]]
@@ -517,7 +578,8 @@ class NcclBackend(CudaPeerBackend):
 class ShardedArrowDecomposition:
     """Convenience wrapper used by bench.py at N > 1: plan + CUDA peer backend + the reference-like calls."""
 
-    def __init__(self, comm, decomposition, width: int, k: int, device: int = 0, exchange: str = "p2p"):
+    def __init__(self, comm, decomposition, width: int, k: int, device: int = 0, exchange: str = "p2p",
+                 overlap: bool = False):
         self.comm = comm
         plan = ShardPlan(decomposition, width, comm.Get_rank(), comm.Get_size())
         if exchange == "p2p":
@@ -526,7 +588,7 @@ class ShardedArrowDecomposition:
             be = NcclBackend(comm, device, width, plan)
         else:
             raise ValueError("exchange must be 'p2p' or 'nccl'")
-        self.engine = ShardedArrowEngine(plan, k, be)
+        self.engine = ShardedArrowEngine(plan, k, be, overlap=overlap)
         self.B = self
         self.matrix_index = 0
         self.decomposition_length = plan.L

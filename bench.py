@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--mode", type=str, default="auto", choices=["auto", "fused", "exchange"])
     ap.add_argument("--exchange", type=str, default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU level exchange: NVLink peer pulls (default) or NCCL all-to-all")
+    ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the forward exchange with the level-0 SpMM (1/0)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-blocks", type=int, default=0)
@@ -180,7 +181,8 @@ def run_b200(a):
     comm = comm_mod.world_comm()
     if world > 1:
         from arrow_matrix_b200.sharded import ShardedArrowDecomposition
-        arrow = ShardedArrowDecomposition(comm, dec, a.width, a.k, device=local_rank, exchange=a.exchange)
+        arrow = ShardedArrowDecomposition(comm, dec, a.width, a.k, device=local_rank, exchange=a.exchange,
+                                          overlap=bool(a.overlap))
         eng = arrow.engine
     else:
         # the public path: files on disk -> load_decomposition_new -> initialize -> load blocks
@@ -315,7 +317,7 @@ def run_b200(a):
         line = {"metric": "iterated SpMM GFLOP/s (k=%d)" % a.k, "value": flops / ms_step / 1e6, "unit": "GFLOP/s",
                 "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(a), "mode": eng.mode, "l2": "inputs larger than L2 (features 5.12 GB per pass at the default size); no flush",
+                "config": {"workload": workload_name(a), "mode": eng.mode, "overlap": bool(getattr(eng, "overlap", False)), "l2": "inputs larger than L2 (features 5.12 GB per pass at the default size); no flush",
                            "total_nnz": int(eng.total_nnz), "setup_s": round(t_setup, 1)},
                 "hbm_gbs_effective": alg_bytes / ms_step / 1e6, "algorithmic_bytes_per_step": alg_bytes,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}

@@ -113,6 +113,10 @@ int  arrow_dense_h2d_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64
 int  arrow_dense_d2h_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, float *host);
 int  arrow_lane_wait(arrow_ctx *ctx, int waiting_lane, int signalling_lane);
 int  arrow_lane_sync(arrow_ctx *ctx, int lane);
+/* Select the lane on which the following arrow_gather_rows[_multi] / arrow_peer_barrier / arrow_dense_copy calls
+ * are launched (arrow_spmm always runs on the main lane).  Used to overlap the NVLink exchange of one level with
+ * the SpMM of another; a barrier issued on lane L must use flag tiles reserved for lane L. */
+int  arrow_set_lane(arrow_ctx *ctx, int lane);
 /* Named events for finer ordering between lanes (waiting on a never-recorded event is a no-op). */
 #define ARROW_MAX_EVENTS 16
 int  arrow_event_record(arrow_ctx *ctx, int event, int lane);

@@ -50,7 +50,13 @@ class GlooNumpyBackend:
     def fill(self, tile, v):
         tile[:] = v
 
-    def barrier(self):
+    def side_begin(self):
+        pass
+
+    def side_join(self):
+        pass
+
+    def barrier(self, side=False):
         self.snap = self.comm.allgather([[t.copy() for t in pair] for pair in self.tiles])
         self.n_barriers += 1
 
@@ -63,7 +69,7 @@ class GlooNumpyBackend:
     def _tile(self, g, level, which):
         return self.tiles[level][which] if g == self.rank else self.snap[g][level][which]
 
-    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True):
+    def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True, side=False):
         d = self.tiles[dst[0]][dst[1]]
         m = row_map.m
         for g in range(self.world):

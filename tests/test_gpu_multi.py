@@ -41,7 +41,8 @@ def _worker(rank, world, port, case, exchange, q):
         w, t0, k, levels, nested = {"L2k128": (128, 9, 128, 2, True), "L3k16": (64, 11, 16, 3, True),
                                     "L3stale_k6": (32, 6, 6, 3, False)}[case]
         dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600)
-        arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank, exchange=exchange)
+        arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank, exchange=exchange.split("+")[0],
+                                          overlap=exchange.endswith("+overlap"))
         eng = arrow.engine
         po = oracle.ReferenceProtocolOracle(dec, w, k)
         rng = np.random.default_rng(2)
@@ -71,7 +72,7 @@ def _worker(rank, world, port, case, exchange, q):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "p2p+overlap", "nccl"])
 @pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6"])
 def test_sharded_engine_on_gpus(case, exchange):
     import torch.multiprocessing as mp

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, q):
+def _worker(rank, world, port, case, q, overlap=False):
     try:
         sys.path.insert(0, ROOT)
         import torch.distributed as dist
@@ -45,7 +45,8 @@ def _worker(rank, world, port, case, q):
             n0 = t0 * w
             Xs = [synth.generate_dense_matrix(n0, k, np.float32, rng), None, synth.generate_dense_matrix(n0, k, np.float32, rng)]
         plan = ShardPlan(dec, w, rank, world)
-        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w))
+        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w), overlap=overlap)
+        assert eng.overlap == overlap
         po = oracle.ReferenceProtocolOracle(dec, w, k)
         assert eng.total_nnz == sum(M.nnz for M in po.mats)
         sh0 = plan.levels[0]
@@ -69,14 +70,16 @@ def _worker(rank, world, port, case, q):
         q.put((rank, "FAIL: " + traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("case", ["L2", "L3", "L3stale", "small", "golden:slim_L2_random_k4", "golden:slim_L3_nonnested_k3"])
-def test_sharded_engine_over_gloo(world, case):
+@pytest.mark.parametrize("world,case,overlap", [(w, c, False) for w in (2, 3) for c in
+                                                ["L2", "L3", "L3stale", "small", "golden:slim_L2_random_k4",
+                                                 "golden:slim_L3_nonnested_k3"]] +
+                         [(2, "L3", True), (3, "L2", True), (3, "L3stale", True)])
+def test_sharded_engine_over_gloo(world, case, overlap):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=180) for _ in procs]
