@@ -22,7 +22,7 @@ IPC_HANDLE_BYTES = 80
 
 EXPORTS = [
     "arrow_b200_abi_version", "arrow_ctx_create", "arrow_ctx_destroy", "arrow_last_error", "arrow_sync",
-    "arrow_device_info", "arrow_set_tuning",
+    "arrow_device_info", "arrow_set_tuning", "arrow_set_option",
     "arrow_csr_upload", "arrow_csr_free", "arrow_csr_info", "arrow_csr_remap_columns",
     "arrow_map_upload", "arrow_map_free", "arrow_map_compose", "arrow_map_invert", "arrow_map_d2h",
     "arrow_dense_alloc", "arrow_dense_free", "arrow_dense_fill", "arrow_dense_h2d", "arrow_dense_d2h",
@@ -66,6 +66,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         "arrow_sync": (c_int, [P]),
         "arrow_device_info": (c_int, [P, pI, pI64, pI64]),
         "arrow_set_tuning": (c_int, [P, I, I]),
+        "arrow_set_option": (c_int, [P, I, I]),
         "arrow_csr_upload": (c_int, [P, I64, I64, I64, P, I, P, I, P, pI]),
         "arrow_csr_free": (c_int, [P, I]),
         "arrow_csr_info": (c_int, [P, I, pI64, pI64, pI64, pI64, pI64]),
@@ -182,6 +183,11 @@ class Context:
 
     def set_tuning(self, long_row_threshold: int, long_row_segment: int):
         self._check(self.lib.arrow_set_tuning(self._h, int(long_row_threshold), int(long_row_segment)))
+
+    OPT_L2_HINTS_PLAIN, OPT_L2_HINTS_FUSED = 1, 2
+
+    def set_option(self, option: int, value: int):
+        self._check(self.lib.arrow_set_option(self._h, int(option), int(value)))
 
     # -- sparse -----------------------------------------------------------------------------
     def csr_upload(self, n_rows: int, n_cols: int, indptr: np.ndarray, indices: np.ndarray,

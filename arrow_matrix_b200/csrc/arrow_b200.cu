@@ -96,6 +96,8 @@ struct arrow_ctx {
     int64_t launches = 0;
     int long_threshold = 512;
     int long_segment = 2048;
+    int l2_hints_plain = 3;           // arrow_set_option(ARROW_OPT_L2_HINTS_PLAIN)
+    int l2_hints_fused = 0;           // arrow_set_option(ARROW_OPT_L2_HINTS_FUSED)
     float *long_scratch = nullptr;    // [slots][k] partial sums of long-row segments
     size_t long_scratch_bytes = 0;
     void *flush_buf = nullptr;
@@ -404,6 +406,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ float4 ldg_f4_hint(const float4 *ptr, uint64_t pol) {
     float4 r;
     asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
@@ -581,6 +588,7 @@ struct TileArgs {
     int n_tiles;
     int skip;            // indices may hold -1
     int *ticket;         // dynamic tile scheduler (zeroed before the launch)
+    int l2_hints;        // bit 0: X gathers evict_last, bit 1: CSR / C streams evict_first
 };
 
 template <int G, int VPL, bool ROWMAP, bool ACC>
@@ -600,8 +608,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
     const int k4 = a.k4;
     const float4 *__restrict__ Xl = reinterpret_cast<const float4 *>(a.X) + gl;
     float4 *__restrict__ Cl = reinterpret_cast<float4 *>(a.C) + gl;
-    const uint64_t pol_keep = l2_policy_evict_last();
-    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = (t.l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const uint64_t pol_stream = (t.l2_hints & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -1193,6 +1201,15 @@ int arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segmen
     return ARROW_OK;
 }
 
+int arrow_set_option(arrow_ctx *ctx, int option, int value) {
+    CHECK_CTX(ctx);
+    switch (option) {
+        case ARROW_OPT_L2_HINTS_PLAIN: ctx->l2_hints_plain = value & 3; return ARROW_OK;
+        case ARROW_OPT_L2_HINTS_FUSED: ctx->l2_hints_fused = value & 3; return ARROW_OK;
+        default: return fail(ctx, ARROW_ERR_ARG, "unknown option %d", option);
+    }
+}
+
 // ---- sparse -------------------------------------------------------------------------------------
 static int build_long_rows(arrow_ctx *ctx, Csr &c, const std::vector<int> &h_indptr) {
     // host pass over the (rebased) row pointer: rows above the threshold become segment tasks
@@ -1675,6 +1692,7 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
             t.n_tiles = A->n_tiles;
             t.skip = A->may_skip ? 1 : 0;
             t.ticket = ctx->tile_ticket;
+            t.l2_hints = (rm != nullptr || acc) ? ctx->l2_hints_fused : ctx->l2_hints_plain;
             int rc = launch_tiles(ctx, t, rm != nullptr, acc, vpl_req);
             if (rc != ARROW_OK) return rc;
         }

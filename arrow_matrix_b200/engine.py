@@ -181,8 +181,7 @@ class ArrowEngine:
 
     def spmm_level(self, level: int):
         """One level's arrow product on its current features (``B.spmm()`` of that level)."""
-        if self.mode != "exchange":
-            self.set_mode("exchange")
+        self.ensure_level_tiles()
         st = self.levels[level]
         out = 1 - st.xi
         self.ctx.spmm(st.csr, st.bufs[st.xi], st.bufs[out], variant=self.variant)

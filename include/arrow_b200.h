@@ -63,6 +63,11 @@ const char *arrow_last_error(const arrow_ctx *ctx);      /* ctx may be NULL: las
 int  arrow_sync(arrow_ctx *ctx);
 int  arrow_device_info(arrow_ctx *ctx, int *sm_count, int64_t *free_bytes, int64_t *total_bytes);
 int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segment);
+/* Tuning knobs.  L2 hint masks of the tile kernel: bit 0 = X gathers evict_last, bit 1 = CSR and C streams
+ * evict_first; PLAIN applies to C = A X launches, FUSED to launches with a row map or ARROW_ACCUMULATE. */
+#define ARROW_OPT_L2_HINTS_PLAIN 1
+#define ARROW_OPT_L2_HINTS_FUSED 2
+int  arrow_set_option(arrow_ctx *ctx, int option, int value);
 
 /* ---- sparse blocks (replaces _sp2cp, sp2cp.py:6-16: uploaded once, resident) ----------------- */
 /* indptr has n_rows+1 entries of indptr_bytes (4 or 8) each and may start at any base value
