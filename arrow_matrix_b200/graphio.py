@@ -131,7 +131,12 @@ def load_decomposition_new(filename: str, width: int = None, block_diagonal: boo
             if mem_map:
                 B = (data, indices, indptr)
             else:
-                B = sparse.csr_matrix((data, indices, indptr))
+                # the reference lets SciPy infer the shape (graphio.py:302), which shrinks the column count when the
+                # trailing vertices are isolated; levels are square adjacency matrices, so state that explicitly
+                n = indptr.size - 1
+                square = indices.size == 0 or int(indices.max()) < n
+                B = sparse.csr_matrix((data, indices, indptr), shape=(n, n)) if square \
+                    else sparse.csr_matrix((data, indices, indptr))
             perm = None
             if not no_permutation:
                 perm = np.load(format_path(filename, width, i, block_diagonal,
