@@ -340,9 +340,15 @@ class ShardedArrowEngine:
 # CUDA backend: NVLink peer memory through CUDA IPC
 # ------------------------------------------------------------------------------------------------------
 class CudaPeerBackend:
-    def __init__(self, comm, device: int, width: int, stream: Optional[int] = None):
+    def __init__(self, comm, device: int, width: int, stream: Optional[int] = None, plan: Optional[ShardPlan] = None):
+        """``plan`` given  -> packed exchange (default): rows are packed locally in the receiver's row order and the
+        receiver reads its peers' contiguous regions (sequential NVLink reads).  ``plan=None`` -> direct pulls of
+        individual rows at random peer addresses; measured on B200: fine while the peer range stays under ~1 GB
+        (669 GB/s), collapsing to ~100 GB/s at 2.5 GB (TLB misses on the NVLink path)."""
         from . import _lib
         self.width = int(width)
+        self.plan = plan
+        self._xtab = {}
         self._lib = _lib
         self.comm = comm
         self.rank, self.world = comm.Get_rank(), comm.Get_size()
@@ -370,20 +376,30 @@ class CudaPeerBackend:
                 pair.append(pos)
                 pos += -(-(r * k) // align) * align
             offs.append(pair)
+        self._send_off, self._send_rows = pos, 0
+        if self.plan is not None:
+            # one shared send buffer (exchanges are separated by barriers): the largest pack of any exchange
+            for lvl in range(self.plan.L):
+                for fwd in (True, False):
+                    if (fwd and lvl == 0) or (not fwd and lvl == self.plan.L - 1):
+                        continue
+                    self._send_rows = max(self._send_rows, int(self.plan.a2a_tables(lvl, fwd)["send_counts"].sum()))
+            pos += -(-(max(self._send_rows, 1) * k) // align) * align
         arena_rows = max(-(-pos // 64), (2 << 20) // 256)       # >= 2 MiB so the driver gives it its own block
         self._arena = ctx.dense_alloc(arena_rows, 64)
         ctx.sync()
-        mine = dict(handle=self._arena.ipc_export(), arena_rows=arena_rows, offs=offs, rows=list(rows_per_level))
+        mine = dict(handle=self._arena.ipc_export(), arena_rows=arena_rows, offs=offs, rows=list(rows_per_level),
+                    send_off=self._send_off, send_rows=self._send_rows)
         everyone = self.comm.allgather(mine)
-        self._peer, self._flags = [], []
+        self._peer, self._flags, self._flags_side, self._arenas, self._arena_base = [], [], [], [], []
         for g, info in enumerate(everyone):
             arena = self._arena if g == self.rank else ctx.ipc_import(info["handle"], info["arena_rows"], 64)
+            self._arenas.append(arena)
             base = arena.device_ptr()
+            self._arena_base.append((base, info["send_off"]))
             self._flags.append(ctx.dense_wrap(base, 1, 64))
-            self._flags_side = getattr(self, "_flags_side", []) + [ctx.dense_wrap(base + 64 * 4, 1, 64)]
+            self._flags_side.append(ctx.dense_wrap(base + 64 * 4, 1, 64))
             self._peer.append([[ctx.dense_wrap(base + o * 4, r, k) for o in pair] for pair, r in zip(info["offs"], info["rows"])])
-            if g != self.rank:
-                self._imported = getattr(self, "_imported", []) + [arena]
         self._tiles = self._peer[self.rank]
         self._views = {}
         return self._tiles
@@ -437,6 +453,8 @@ class CudaPeerBackend:
         self.ctx.spmm(A, X, C)
 
     def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True, side=False):
+        if self.plan is not None:
+            return self._packed_exchange(dst, dst_off, src, accumulate, forward, side)
         lvl, which = dst
         n = row_map.n
         if n == 0:
@@ -459,6 +477,59 @@ class CudaPeerBackend:
             hoff = self._hoff(g)
             srcs.append(self._view(g, src[0], src[1], hoff if own > 0 else 0, max(own, 0)))
         self.ctx.gather_rows_multi(d, srcs, [int(b) for b in src_bounds], row_map, accumulate=accumulate)
+
+    # -- packed exchange -------------------------------------------------------------------------------------
+    def _exchange_table(self, dst_level: int, forward: bool):
+        key = (dst_level, forward)
+        t = self._xtab.get(key)
+        if t is None:
+            raw = self.plan.a2a_tables(dst_level, forward)
+            counts = self.comm.allgather([int(c) for c in raw["send_counts"]])       # counts[s][d]
+            src_level = dst_level - 1 if forward else dst_level + 1
+            n_send, n_recv = int(raw["send_counts"].sum()), int(raw["recv_counts"].sum())
+            # where, inside peer s's send buffer, the rows meant for me start
+            region = [sum(counts[s][:self.rank]) for s in range(self.world)]
+            rb = np.concatenate([[0], np.cumsum(raw["recv_counts"])]).astype(np.int64)
+            t = dict(n_send=n_send, n_recv=n_recv, region=region, recv_bounds=[int(b) for b in rb],
+                     recv_counts=[int(c) for c in raw["recv_counts"]],
+                     pack=self.ctx.map_upload(raw["pack"], max(self.plan.levels[src_level].own_rows, 1)),
+                     unpack=self.ctx.map_upload(raw["unpack"], max(n_recv, 1)))
+            self._xtab[key] = t
+        return t
+
+    def _raw_view(self, g: int, float_off: int, rows: int):
+        key = ("raw", g, float_off, rows)
+        v = self._views.get(key)
+        if v is None:
+            v = self.ctx.dense_wrap(self._arena_base[g][0] + float_off * 4, rows, self.k)
+            self._views[key] = v
+        return v
+
+    def _packed_exchange(self, dst, dst_off, src, accumulate, forward, side):
+        t = self._exchange_table(dst[0], forward)
+        src_sh = self.plan.levels[src[0]]
+        if side:
+            self.ctx.set_lane(self.SIDE)
+        try:
+            if t["n_send"] > 0:        # pack my source rows, grouped by destination rank, in the destination's row order
+                self.ctx.gather_rows(self._raw_view(self.rank, self._send_off, t["n_send"]),
+                                     self._view(self.rank, src[0], src[1], src_sh.hoff, src_sh.own_rows), t["pack"])
+        finally:
+            if side:
+                self.ctx.set_lane(0)
+        self.barrier(side)                 # every peer's pack is complete
+        n = self.plan.levels[dst[0]].own_rows
+        if n > 0 and t["n_recv"] > 0:
+            if side:
+                self.ctx.set_lane(self.SIDE)
+            try:
+                srcs = [self._raw_view(g, self._arena_base[g][1] + t["region"][g] * self.k, t["recv_counts"][g])
+                        for g in range(self.world)]
+                self.ctx.gather_rows_multi(self._view(self.rank, dst[0], dst[1], dst_off, n), srcs, t["recv_bounds"],
+                                           t["unpack"], accumulate=accumulate)
+            finally:
+                if side:
+                    self.ctx.set_lane(0)
 
     def _hoff(self, g: int) -> int:
         return self.width if g > 0 else 0
@@ -504,7 +575,7 @@ class NcclBackend(CudaPeerBackend):
         # run on torch's current stream so kernels and NCCL collectives are ordered; torch's default stream is the
         # legacy default stream (handle 0), which CUDA also names cudaStreamLegacy = 0x1
         super().__init__(comm, device, width, stream=torch.cuda.current_stream().cuda_stream or 1)
-        self.plan = plan
+        self.plan_nccl = plan
         self._tables = {}
         self._bufs = {}
 
@@ -532,12 +603,12 @@ class NcclBackend(CudaPeerBackend):
         key = (dst_level, forward)
         t = self._tables.get(key)
         if t is None:
-            raw = self.plan.a2a_tables(dst_level, forward)
+            raw = self.plan_nccl.a2a_tables(dst_level, forward)
             n_send, n_recv = int(raw["send_counts"].sum()), int(raw["recv_counts"].sum())
             src_level = dst_level - 1 if forward else dst_level + 1
             t = dict(send_counts=[int(c) for c in raw["send_counts"]], recv_counts=[int(c) for c in raw["recv_counts"]],
                      n_send=n_send, n_recv=n_recv,
-                     pack=self.ctx.map_upload(raw["pack"], max(self.plan.levels[src_level].own_rows, 1)),
+                     pack=self.ctx.map_upload(raw["pack"], max(self.plan_nccl.levels[src_level].own_rows, 1)),
                      unpack=self.ctx.map_upload(raw["unpack"], max(n_recv, 1)),
                      sendbuf=self.ctx.dense_alloc(max(n_send, 1), self.k), recvbuf=self.ctx.dense_alloc(max(n_recv, 1), self.k))
             self._tables[key] = t
@@ -546,7 +617,7 @@ class NcclBackend(CudaPeerBackend):
     def pull_rows(self, dst, dst_off, src, src_bounds, row_map, accumulate, forward=True, side=False):
         import torch.distributed as dist
         t = self._table(dst[0], forward)
-        src_sh = self.plan.levels[src[0]]
+        src_sh = self.plan_nccl.levels[src[0]]
         if t["n_send"] > 0:
             s_own = self._view(self.rank, src[0], src[1], src_sh.hoff, src_sh.own_rows)
             self.ctx.gather_rows(self._sub(t["sendbuf"], t["n_send"]), s_own, t["pack"])          # pack
@@ -583,11 +654,13 @@ class ShardedArrowDecomposition:
         self.comm = comm
         plan = ShardPlan(decomposition, width, comm.Get_rank(), comm.Get_size())
         if exchange == "p2p":
+            be = CudaPeerBackend(comm, device, width, plan=plan)
+        elif exchange == "p2p-direct":
             be = CudaPeerBackend(comm, device, width)
         elif exchange == "nccl":
             be = NcclBackend(comm, device, width, plan)
         else:
-            raise ValueError("exchange must be 'p2p' or 'nccl'")
+            raise ValueError("exchange must be 'p2p', 'p2p-direct' or 'nccl'")
         self.engine = ShardedArrowEngine(plan, k, be, overlap=overlap)
         self.B = self
         self.matrix_index = 0

@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--levels", type=int, default=2)
     ap.add_argument("--perm", type=str, default="random", choices=["random", "local", "identity"])
     ap.add_argument("--mode", type=str, default="auto", choices=["auto", "fused", "exchange"])
-    ap.add_argument("--exchange", type=str, default="p2p", choices=["p2p", "nccl"],
+    ap.add_argument("--exchange", type=str, default="p2p", choices=["p2p", "p2p-direct", "nccl"],
                     help="multi-GPU level exchange: NVLink peer pulls (default) or NCCL all-to-all")
     ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the forward exchange with the level-0 SpMM (1/0)")
     ap.add_argument("--l2-hints", type=str, default="", help="plain,fused L2 hint masks of the tile kernel (e.g. 3,0)")

@@ -28,12 +28,16 @@ def timed(name, fn, n=5):
     if rank == 0: print(json.dumps({"phase": name, "ms_max_over_ranks": round(float(t.item()), 3), "ms_rank0": round(ms, 3)}), flush=True)
 timed("barrier", lambda: be.barrier(), 20)
 sh1, sh0 = eng.plan.levels[1], eng.plan.levels[0]
-timed("fwd_pull", lambda: be.pull_rows(dst=(1, eng.ci[1]), dst_off=sh1.hoff, src=(0, eng.xi[0]), src_bounds=sh0.bounds, row_map=eng.fwd[1], accumulate=False, forward=True))
+def fwd():
+    be.pull_rows(dst=(1, eng.ci[1]), dst_off=sh1.hoff, src=(0, eng.xi[0]), src_bounds=sh0.bounds, row_map=eng.fwd[1], accumulate=False, forward=True); be.barrier()
+timed("fwd_exchange+barrier", fwd)
 timed("bcast_head_x2", lambda: [be.bcast_head((j, eng.xi[j]), 10000) for j in range(2)])
 timed("spmm_L0", lambda: be.spmm(eng.mats[0], eng.tiles[0][0], eng.tiles[0][1]))
 timed("spmm_L1", lambda: be.spmm(eng.mats[1], eng.tiles[1][0], eng.tiles[1][1]))
 timed("reduce_head_x2", lambda: [be.reduce_head((j, 1), 10000) for j in range(2)])
-timed("bwd_pull", lambda: be.pull_rows(dst=(0, 1), dst_off=sh0.hoff, src=(1, 1), src_bounds=sh1.bounds, row_map=eng.bwd[0], accumulate=True, forward=False))
+def bwd():
+    be.pull_rows(dst=(0, 1), dst_off=sh0.hoff, src=(1, 1), src_bounds=sh1.bounds, row_map=eng.bwd[0], accumulate=True, forward=False); be.barrier()
+timed("bwd_exchange+barrier", bwd)
 def full():
     eng.rewind_features(); eng.step()
 timed("full_step", full)

@@ -72,7 +72,7 @@ def _worker(rank, world, port, case, exchange, q):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("exchange", ["p2p", "p2p+overlap", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "p2p+overlap", "p2p-direct", "nccl"])
 @pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6"])
 def test_sharded_engine_on_gpus(case, exchange):
     import torch.multiprocessing as mp
