@@ -102,12 +102,12 @@ struct arrow_ctx {
     size_t long_scratch_bytes = 0;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
-    unsigned int barrier_epoch[3] = {0, 0, 0};   // one epoch counter per lane (each lane has its own flag set)
+    unsigned int barrier_epoch[ARROW_N_LANES] = {};   // one epoch counter per lane (each lane has its own flag set)
     int cur_lane = 0;                             // lane used by gather / barrier / copy launches (arrow_set_lane)
     int *dev_status = nullptr;        // device-side status word (barrier timeout)
     int *tile_ticket = nullptr;       // device counter of the dynamic tile scheduler
-    cudaStream_t lanes[ARROW_N_LANES] = {nullptr, nullptr, nullptr};   // lane 0 = main stream
-    cudaEvent_t lane_events[ARROW_N_LANES] = {nullptr, nullptr, nullptr};
+    cudaStream_t lanes[ARROW_N_LANES] = {};   // lane 0 = main stream
+    cudaEvent_t lane_events[ARROW_N_LANES] = {};
     cudaEvent_t user_events[ARROW_MAX_EVENTS] = {};
 };
 

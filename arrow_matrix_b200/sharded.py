@@ -175,29 +175,66 @@ class ShardedArrowEngine:
             next_rows = plan.levels[sh.level + 1].rows_global if sh.level < self.L - 1 else 0
             self.fwd.append(be.map_upload(sh.fwd_map, prev_rows) if sh.fwd_map is not None else None)
             self.bwd.append(be.map_upload(sh.bwd_map, next_rows) if sh.bwd_map is not None else None)
-        # two ping-pong tiles per level, shared with the peers
-        self.tiles = be.alloc_shared_tiles([max(sh.local_rows, 1) for sh in plan.levels], self.k)
+        # two ping-pong tiles per level, shared with the peers; level 0 gets a second pair for the streaming
+        # iteration (upload of step i+1 / download of step i-1 overlap the compute of step i)
+        self.tiles = be.alloc_shared_tiles([max(sh.local_rows, 1) for sh in plan.levels], self.k,
+                                           tiles_per_level=[4] + [2] * (self.L - 1))
         self.xi = [0] * self.L
         self.ci = [0] * self.L
+        self._pair = 0                      # which level-0 pair is active: tile index = 2*pair + {0,1}
         self.total_nnz_local = sum(sh.nnz for sh in plan.levels)
         self.total_nnz = int(be.allreduce_sum(self.total_nnz_local))
         self.local_rows = plan.levels[0].own_rows
         be.barrier()
 
     # -- features / results: this rank's own rows of level 0 ------------------------------------------------
+    def _other(self, level: int, idx: int) -> int:
+        """the partner tile of ``idx`` inside its ping-pong pair"""
+        return idx ^ 1
+
     def set_features(self, X: np.ndarray, sync: bool = True):
         sh = self.plan.levels[0]
         if X.shape != (sh.own_rows, self.k):
             raise ValueError(f"rank {self.rank}: expected features of shape {(sh.own_rows, self.k)}, got {X.shape}")
         if self.xi[0] == self.ci[0]:
-            self.xi[0] = 1 - self.ci[0]
+            self.xi[0] = self._other(0, self.ci[0])
         self.be.h2d(self.tiles[0][self.xi[0]], sh.hoff, X)
         if sync:
             self.be.sync()
 
     def rewind_features(self):
         if self.xi[0] == self.ci[0]:
-            self.xi[0] = 1 - self.ci[0]
+            self.xi[0] = self._other(0, self.ci[0])
+
+    def stream_step(self, X_host: np.ndarray, out_host: np.ndarray):
+        """Pipelined host-staged iteration on this rank's rows (see ``ArrowEngine.stream_step``): every rank calls
+        it with its own pinned arrays; uploads / step / downloads of consecutive calls overlap."""
+        sh = self.plan.levels[0]
+        if X_host.shape != (sh.own_rows, self.k) or out_host.shape != (sh.own_rows, self.k):
+            raise ValueError(f"rank {self.rank}: expected host arrays of shape {(sh.own_rows, self.k)}")
+        ctx = self.be.ctx
+        p = self._pair
+        self._pair ^= 1
+        EV_H2D, EV_MAIN, EV_D2H = 3 * p, 3 * p + 1, 3 * p + 2
+        LANE_H2D, LANE_D2H = 1, 2
+        x_tile, c_tile = self.tiles[0][2 * p], self.tiles[0][2 * p + 1]
+        ctx.event_wait(EV_MAIN, LANE_H2D)
+        ctx.h2d_lane(LANE_H2D, x_tile, X_host, row0=sh.hoff)
+        ctx.event_record(EV_H2D, LANE_H2D)
+        ctx.event_wait(EV_H2D, 0)
+        ctx.event_wait(EV_D2H, 0)
+        self.xi[0], self.ci[0] = 2 * p, 2 * p + 1
+        self.step()
+        ctx.event_record(EV_MAIN, 0)
+        ctx.event_wait(EV_MAIN, LANE_D2H)
+        ctx.d2h_lane(LANE_D2H, self.tiles[0][self.ci[0]], out_host, row0=sh.hoff)
+        ctx.event_record(EV_D2H, LANE_D2H)
+
+    def stream_drain(self):
+        ctx = self.be.ctx
+        ctx.lane_sync(1)
+        ctx.sync()
+        ctx.lane_sync(2)
 
     def result(self, level: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
         sh = self.plan.levels[level]
@@ -228,7 +265,7 @@ class ShardedArrowEngine:
         hr = min(self.width, sh.rows_global)
         be.barrier()
         be.bcast_head((level, self.xi[level]), hr)
-        out = 1 - self.xi[level]
+        out = self._other(level, self.xi[level])
         if self.mats[level] is not None and sh.local_rows > 0:
             be.spmm(self.mats[level], self.tiles[level][self.xi[level]], self.tiles[level][out])
         self.ci[level] = out
@@ -240,7 +277,10 @@ class ShardedArrowEngine:
         pass                                                    # the sharded engine always materialises them
 
     def sync(self):
-        self.be.sync()
+        if getattr(self.be, "ctx", None) is not None:
+            self.stream_drain()             # copy lanes + main stream
+        else:
+            self.be.sync()
 
     def close(self):
         if getattr(self.be, "ctx", None) is not None:
@@ -264,7 +304,7 @@ class ShardedArrowEngine:
 
     def spmm(self):
         for j in range(self.L):
-            out = 1 - self.xi[j]
+            out = self._other(j, self.xi[j])
             if self.mats[j] is not None and self.plan.levels[j].local_rows > 0:
                 self.be.spmm(self.mats[j], self.tiles[j][self.xi[j]], self.tiles[j][out])
             self.ci[j] = out
@@ -286,7 +326,7 @@ class ShardedArrowEngine:
                 be.barrier()
 
     def _spmm_one(self, j: int):
-        out = 1 - self.xi[j]
+        out = self._other(j, self.xi[j])
         if self.mats[j] is not None and self.plan.levels[j].local_rows > 0:
             self.be.spmm(self.mats[j], self.tiles[j][self.xi[j]], self.tiles[j][out])
         self.ci[j] = out
@@ -364,15 +404,16 @@ class CudaPeerBackend:
     def map_upload(self, m, limit):
         return self.ctx.map_upload(m, limit)
 
-    def alloc_shared_tiles(self, rows_per_level: Sequence[int], k: int):
-        """One arena per rank (a single cudaMalloc => a single IPC handle): two ping-pong tiles per level + flags."""
+    def alloc_shared_tiles(self, rows_per_level: Sequence[int], k: int, tiles_per_level: Optional[Sequence[int]] = None):
+        """One arena per rank (a single cudaMalloc => a single IPC handle): ping-pong tiles per level + flags."""
         ctx = self.ctx
         self.k = k
+        tiles_per_level = list(tiles_per_level) if tiles_per_level is not None else [2] * len(rows_per_level)
         align = 64                                              # floats (256 bytes)
         offs, pos = [], 128                                     # first 128 floats: barrier flags of the two lanes
-        for r in rows_per_level:
+        for r, nt in zip(rows_per_level, tiles_per_level):
             pair = []
-            for _ in range(2):
+            for _ in range(nt):
                 pair.append(pos)
                 pos += -(-(r * k) // align) * align
             offs.append(pair)
@@ -426,7 +467,7 @@ class CudaPeerBackend:
     def sync(self):
         self.ctx.sync()
 
-    SIDE = 1            # lane id of the side stream
+    SIDE = 3            # lane id of the side stream (lanes 1 and 2 are the host copy lanes)
 
     def barrier(self, side: bool = False):
         if self.world <= 1:
@@ -579,9 +620,10 @@ class NcclBackend(CudaPeerBackend):
         self._tables = {}
         self._bufs = {}
 
-    def alloc_shared_tiles(self, rows_per_level, k):
+    def alloc_shared_tiles(self, rows_per_level, k, tiles_per_level=None):
         self.k = k
-        self._tiles = [[self.ctx.dense_alloc(r, k), self.ctx.dense_alloc(r, k)] for r in rows_per_level]
+        tiles_per_level = list(tiles_per_level) if tiles_per_level is not None else [2] * len(rows_per_level)
+        self._tiles = [[self.ctx.dense_alloc(r, k) for _ in range(nt)] for r, nt in zip(rows_per_level, tiles_per_level)]
         self._peer = [None] * self.world
         self._peer[self.rank] = self._tiles
         self._views = {}
@@ -675,5 +717,8 @@ class ShardedArrowDecomposition:
     def step(self):
         self.engine.step()
 
+    def step_stream(self, X_host, out_host):
+        self.engine.stream_step(X_host, out_host)
+
     def synchronize(self):
-        self.engine.be.sync()
+        self.engine.sync()

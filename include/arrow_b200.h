@@ -113,7 +113,8 @@ int  arrow_dense_wrap(arrow_ctx *ctx, void *device_ptr, int64_t rows, int k, int
 #define ARROW_LANE_MAIN 0
 #define ARROW_LANE_H2D  1
 #define ARROW_LANE_D2H  2
-#define ARROW_N_LANES   3
+#define ARROW_LANE_SIDE 3   /* compute-side lane: exchange kernels overlapping the main lane's SpMM */
+#define ARROW_N_LANES   4
 int  arrow_dense_h2d_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, const float *host);
 int  arrow_dense_d2h_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, float *host);
 int  arrow_lane_wait(arrow_ctx *ctx, int waiting_lane, int signalling_lane);

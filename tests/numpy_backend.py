@@ -30,9 +30,10 @@ class GlooNumpyBackend:
     def map_upload(self, m, limit):
         return _Map(m, limit)
 
-    def alloc_shared_tiles(self, rows_per_level, k):
+    def alloc_shared_tiles(self, rows_per_level, k, tiles_per_level=None):
         self.k = k
-        self.tiles = [[np.zeros((r, k), np.float32), np.zeros((r, k), np.float32)] for r in rows_per_level]
+        tiles_per_level = tiles_per_level or [2] * len(rows_per_level)
+        self.tiles = [[np.zeros((r, k), np.float32) for _ in range(nt)] for r, nt in zip(rows_per_level, tiles_per_level)]
         return self.tiles
 
     def h2d(self, tile, off, X):

@@ -88,3 +88,64 @@ def test_sharded_engine_on_gpus(case, exchange):
         p.join(60)
     bad = [f"rank {r}: {m}" for r, m in sorted(results) if m != "ok"]
     assert not bad, "\n".join(bad)
+
+
+def _stream_worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                device_id=torch.device("cuda", rank))
+        from arrow_matrix_b200 import _lib, synth
+        from arrow_matrix_b200.comm import world_comm
+        from arrow_matrix_b200.sharded import ShardedArrowDecomposition
+        w, t0, k = 64, 10, 32
+        dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=12)
+        rng = np.random.default_rng(3)
+        Xs = [synth.generate_dense_matrix(t0 * w, k, np.float32, rng) for _ in range(5)]
+        arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank, overlap=True)
+        sh0 = arrow.engine.plan.levels[0]
+        ref = []
+        for X in Xs:
+            arrow.set_features(X[sh0.r0:sh0.r1])
+            arrow.step()
+            ref.append(arrow.result_tile())
+        n = sh0.own_rows
+        hx = [_lib.PinnedArray((n, k)) for _ in range(2)]
+        hc = [_lib.PinnedArray((n, k)) for _ in range(2)]
+        got = []
+        for i, X in enumerate(Xs):
+            if i >= 2:
+                arrow.synchronize()
+                got.append(hc[i % 2].array.copy())
+            hx[i % 2].array[:] = X[sh0.r0:sh0.r1]
+            arrow.step_stream(hx[i % 2].array, hc[i % 2].array)
+        arrow.synchronize()
+        got += [hc[(len(Xs) - 2) % 2].array.copy(), hc[(len(Xs) - 1) % 2].array.copy()]
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except BaseException:     # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
+def test_sharded_stream_step():
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stream_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    bad = [f"rank {r}: {m}" for r, m in sorted(results) if m != "ok"]
+    assert not bad, "\n".join(bad)
