@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { # N exchange overlap perm tag
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port 29521 \
+     bench.py --gpus $1 --steps 20 --warmup 5 --exchange $2 --overlap $3 --perm $4 --no-cpu 2>&1 | tee gpurun_out/bench12_$5.log | tail -1 | python -c "
+import sys, json
+try:
+    d=json.loads(sys.stdin.read()); print('$5', 'ms/step', round(d['ms_per_step'],3), 'GF', round(d['value']), 'e2e ms', round(d['e2e']['ms_per_step'],1), 'e2e GF', round(d['e2e']['value']), 'launches', d['gpu_launches'])
+except Exception as e:
+    print('$5 FAILED', e)"
+}
+run 8 p2p 1 random n8_p2p_ov1
+run 8 p2p 0 random n8_p2p_ov0
+run 4 p2p 1 random n4_p2p_ov1
+run 8 nccl 0 random n8_nccl
+run 8 p2p 1 local n8_p2p_local
+tail -5 gpurun_out/bench12_n8_p2p_ov1.log | cut -c1-300
