@@ -65,6 +65,8 @@ struct Csr {
     // row tiles for the CSR-streaming kernel: {row_begin, row_end, nnz_begin, nnz_end}
     int4 *tiles = nullptr;
     int n_tiles = 0;
+    int4 *tiles_big = nullptr;        // TILE_ROWS_BIG / TILE_NNZ_BIG variant for narrow feature tiles
+    int n_tiles_big = 0;
     bool live = false;
 };
 
@@ -98,6 +100,7 @@ struct arrow_ctx {
     int long_segment = 2048;
     int l2_hints_plain = 3;           // arrow_set_option(ARROW_OPT_L2_HINTS_PLAIN)
     int l2_hints_fused = 0;           // arrow_set_option(ARROW_OPT_L2_HINTS_FUSED)
+    int big_tiles = 1;                // arrow_set_option(ARROW_OPT_BIG_TILES): 128-row tiles when k <= 32
     float *long_scratch = nullptr;    // [slots][k] partial sums of long-row segments
     size_t long_scratch_bytes = 0;
     void *flush_buf = nullptr;
@@ -576,11 +579,16 @@ __global__ void __launch_bounds__(TMA_WARPS * 32) k_spmm_tma(SpmmArgs a) {
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_ROWS = 64;       // small tiles keep the rows in flight (grid x TILE_ROWS) inside ~4 blocks => L2 hits
 constexpr int TILE_NNZ = 1024;
+constexpr int TILE_ROWS_BIG = 128;  // k <= 32: the panels are small, bigger tiles amortise the per-tile fixed cost
+constexpr int TILE_NNZ_BIG = 2048;
 constexpr int TILE_THREADS = 256;
-constexpr int TILE_PTR_WORDS = TILE_ROWS + 8;          // row pointer slice (+ alignment slack)
-constexpr int TILE_NNZ_WORDS = TILE_NNZ + 8;
-constexpr int TILE_STAGE_WORDS = TILE_PTR_WORDS + 2 * TILE_NNZ_WORDS;
-constexpr size_t TILE_SMEM_BYTES = (size_t)2 * TILE_STAGE_WORDS * 4 + 16;
+template <int TR, int TN>
+struct TileCfg {
+    static constexpr int PTR_WORDS = TR + 8;           // row pointer slice (+ alignment slack)
+    static constexpr int NNZ_WORDS = TN + 8;
+    static constexpr int STAGE_WORDS = PTR_WORDS + 2 * NNZ_WORDS;
+    static constexpr size_t SMEM_BYTES = (size_t)2 * STAGE_WORDS * 4 + 16;
+};
 
 struct TileArgs {
     SpmmArgs a;
@@ -591,8 +599,11 @@ struct TileArgs {
     int l2_hints;        // bit 0: X gathers evict_last, bit 1: CSR / C streams evict_first
 };
 
-template <int G, int VPL, bool ROWMAP, bool ACC>
+template <int G, int VPL, bool ROWMAP, bool ACC, int TR, int TN>
 __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
+    constexpr int TILE_PTR_WORDS = TileCfg<TR, TN>::PTR_WORDS;
+    constexpr int TILE_NNZ_WORDS = TileCfg<TR, TN>::NNZ_WORDS;
+    constexpr int TILE_STAGE_WORDS = TileCfg<TR, TN>::STAGE_WORDS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     int *stage_base = reinterpret_cast<int *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)2 * TILE_STAGE_WORDS * 4);
@@ -1030,32 +1041,33 @@ int launch_tma(arrow_ctx *ctx, const SpmmArgs &a, bool rowmap, bool acc) {
     return ARROW_OK;
 }
 
-template <int G, int VPL>
+template <int G, int VPL, int TR, int TN>
 int launch_tiles_gv(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc) {
+    constexpr size_t SMEM = TileCfg<TR, TN>::SMEM_BYTES;
 #define LAUNCH_TL(KERNEL)                                                                             \
     do {                                                                                              \
         auto fn = KERNEL;                                                                             \
         static bool attr_set = false;                                                                 \
         static int occ = 0;                                                                           \
         if (!attr_set) {                                                                              \
-            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES); \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TILE_THREADS, TILE_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1; \
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);         \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TILE_THREADS, SMEM) != cudaSuccess || occ < 1) occ = 1; \
             attr_set = true;                                                                          \
         }                                                                                             \
         int grid = (int)std::min<long long>((long long)occ * ctx->sm_count, t.n_tiles);               \
-        fn<<<grid, TILE_THREADS, TILE_SMEM_BYTES, ctx->stream>>>(t);                                  \
+        fn<<<grid, TILE_THREADS, SMEM, ctx->stream>>>(t);                                             \
     } while (0)
-    if (rowmap && acc) LAUNCH_TL((k_spmm_tiles<G, VPL, true, true>));
-    else if (rowmap) LAUNCH_TL((k_spmm_tiles<G, VPL, true, false>));
-    else if (acc) LAUNCH_TL((k_spmm_tiles<G, VPL, false, true>));
-    else LAUNCH_TL((k_spmm_tiles<G, VPL, false, false>));
+    if (rowmap && acc) LAUNCH_TL((k_spmm_tiles<G, VPL, true, true, TR, TN>));
+    else if (rowmap) LAUNCH_TL((k_spmm_tiles<G, VPL, true, false, TR, TN>));
+    else if (acc) LAUNCH_TL((k_spmm_tiles<G, VPL, false, true, TR, TN>));
+    else LAUNCH_TL((k_spmm_tiles<G, VPL, false, false, TR, TN>));
 #undef LAUNCH_TL
     ctx->launches++;
     return ARROW_OK;
 }
 
 // (lanes per row, float4 per lane) for a k4 = k/4; vpl_req = 0 picks the default
-int launch_tiles(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc, int vpl_req) {
+int launch_tiles(arrow_ctx *ctx, TileArgs &t, const Csr *A, bool rowmap, bool acc, int vpl_req) {
     const int k4 = t.a.k4;
     int vpl = vpl_req;
     // measured on B200 (profiles/r01_kernel_sweep.md): ~8 lanes per row is the sweet spot
@@ -1065,11 +1077,18 @@ int launch_tiles(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc, int v
     if (lanes > 32) { vpl = (k4 + 31) / 32 <= 2 ? 2 : 4; lanes = (k4 + vpl - 1) / vpl; }
     int g = 1;
     while (g < lanes) g <<= 1;
-#define TL(GG, VV) if (g == GG && vpl == VV) return launch_tiles_gv<GG, VV>(ctx, t, rowmap, acc)
+    const bool big = (k4 <= 8) && ctx->big_tiles && A->n_tiles_big > 0;     // k <= 32
+    if (big) { t.tiles = A->tiles_big; t.n_tiles = A->n_tiles_big; }
+#define TL(GG, VV)                                                                                       \
+    if (g == GG && vpl == VV) return launch_tiles_gv<GG, VV, TILE_ROWS, TILE_NNZ>(ctx, t, rowmap, acc)
+#define TLB(GG, VV)                                                                                      \
+    if (big && g == GG && vpl == VV) return launch_tiles_gv<GG, VV, TILE_ROWS_BIG, TILE_NNZ_BIG>(ctx, t, rowmap, acc)
+    TLB(1, 1); TLB(2, 1); TLB(4, 1); TLB(8, 1); TLB(1, 2); TLB(2, 2); TLB(4, 2); TLB(1, 4); TLB(2, 4);
     TL(1, 1); TL(2, 1); TL(4, 1); TL(8, 1); TL(16, 1); TL(32, 1);
     TL(1, 2); TL(2, 2); TL(4, 2); TL(8, 2); TL(16, 2); TL(32, 2);
     TL(1, 4); TL(2, 4); TL(4, 4); TL(8, 4); TL(16, 4);
 #undef TL
+#undef TLB
     return fail(ctx, ARROW_ERR_UNSUPPORTED, "no tile kernel for k4=%d vpl=%d", k4, vpl);
 }
 
@@ -1148,6 +1167,7 @@ void arrow_ctx_destroy(arrow_ctx *ctx) {
                 cudaFree(c.long_rows);
                 cudaFree(c.long_first);
                 cudaFree(c.tiles);
+                cudaFree(c.tiles_big);
             }
         }
     for (auto &m : ctx->maps)
@@ -1206,6 +1226,7 @@ int arrow_set_option(arrow_ctx *ctx, int option, int value) {
     switch (option) {
         case ARROW_OPT_L2_HINTS_PLAIN: ctx->l2_hints_plain = value & 3; return ARROW_OK;
         case ARROW_OPT_L2_HINTS_FUSED: ctx->l2_hints_fused = value & 3; return ARROW_OK;
+        case ARROW_OPT_BIG_TILES: ctx->big_tiles = value ? 1 : 0; return ARROW_OK;
         default: return fail(ctx, ARROW_ERR_ARG, "unknown option %d", option);
     }
 }
@@ -1228,29 +1249,36 @@ static int build_long_rows(arrow_ctx *ctx, Csr &c, const std::vector<int> &h_ind
         }
     }
     first.push_back((int)tasks.size());
-    // row tiles for k_spmm_tiles: contiguous rows, <= TILE_ROWS rows and <= TILE_NNZ entries, cut around long rows
-    {
+    // row tiles for k_spmm_tiles: contiguous rows, <= rows_cap rows and <= nnz_cap entries, cut around long rows
+    auto build_tiles = [&](int rows_cap, int nnz_cap, int4 **out, int *n_out) -> int {
         std::vector<int4> tiles;
         int64_t r = 0;
         while (r < c.n_rows) {
             const int len0 = h_indptr[r + 1] - h_indptr[r];
             if (len0 > thr) { ++r; continue; }                     // long rows are not tiled
             int64_t e = r;
-            while (e < c.n_rows && e - r < TILE_ROWS) {
+            while (e < c.n_rows && e - r < rows_cap) {
                 const int len = h_indptr[e + 1] - h_indptr[e];
                 if (len > thr) break;
-                if (h_indptr[e + 1] - h_indptr[r] > TILE_NNZ - 4 && e > r) break;
+                if (h_indptr[e + 1] - h_indptr[r] > nnz_cap - 4 && e > r) break;
                 ++e;
             }
             if (e == r) ++e;                                       // a single row always fits: thr <= TILE_NNZ - 8
             tiles.push_back(make_int4((int)r, (int)e, h_indptr[r], h_indptr[e]));
             r = e;
         }
-        c.n_tiles = (int)tiles.size();
+        *n_out = (int)tiles.size();
         if (!tiles.empty()) {
-            CUDA_TRY(ctx, cudaMalloc(&c.tiles, tiles.size() * sizeof(int4)));
-            CUDA_TRY(ctx, cudaMemcpy(c.tiles, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
+            CUDA_TRY(ctx, cudaMalloc(out, tiles.size() * sizeof(int4)));
+            CUDA_TRY(ctx, cudaMemcpy(*out, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice));
         }
+        return ARROW_OK;
+    };
+    {
+        int rc = build_tiles(TILE_ROWS, TILE_NNZ, &c.tiles, &c.n_tiles);
+        if (rc != ARROW_OK) return rc;
+        rc = build_tiles(TILE_ROWS_BIG, TILE_NNZ_BIG, &c.tiles_big, &c.n_tiles_big);
+        if (rc != ARROW_OK) return rc;
     }
     c.max_row_nnz = mx;
     c.long_threshold = thr;
@@ -1368,6 +1396,7 @@ int arrow_csr_free(arrow_ctx *ctx, int csr) {
         cudaFree(c->long_rows);
         cudaFree(c->long_first);
         cudaFree(c->tiles);
+        cudaFree(c->tiles_big);
     }
     *c = Csr();
     return ARROW_OK;
@@ -1693,7 +1722,7 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
             t.skip = A->may_skip ? 1 : 0;
             t.ticket = ctx->tile_ticket;
             t.l2_hints = (rm != nullptr || acc) ? ctx->l2_hints_fused : ctx->l2_hints_plain;
-            int rc = launch_tiles(ctx, t, rm != nullptr, acc, vpl_req);
+            int rc = launch_tiles(ctx, t, A, rm != nullptr, acc, vpl_req);
             if (rc != ARROW_OK) return rc;
         }
     } else if (variant == ARROW_VARIANT_TMA && k >= 32 && k <= 128) {

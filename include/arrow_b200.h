@@ -67,6 +67,7 @@ int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segme
  * evict_first; PLAIN applies to C = A X launches, FUSED to launches with a row map or ARROW_ACCUMULATE. */
 #define ARROW_OPT_L2_HINTS_PLAIN 1
 #define ARROW_OPT_L2_HINTS_FUSED 2
+#define ARROW_OPT_BIG_TILES      3   /* 1 (default): 128-row / 2048-entry CSR tiles when k <= 32 */
 int  arrow_set_option(arrow_ctx *ctx, int option, int value);
 
 /* ---- sparse blocks (replaces _sp2cp, sp2cp.py:6-16: uploaded once, resident) ----------------- */

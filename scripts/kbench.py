@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--uniform", action="store_true", help="utils.generate_sparse_matrix recipe instead of arrow shaped")
     ap.add_argument("--peak", type=float, default=0.0)
+    ap.add_argument("--big-tiles", type=int, default=1)
     args = ap.parse_args()
 
     peak = args.peak
@@ -41,6 +42,7 @@ def main():
         A = synth.arrow_csr(n, args.width, args.blocks, rng)
     print(f"# generated {n}x{n} nnz={A.nnz} in {time.time() - t0:.1f}s", flush=True)
     ctx = _lib.Context(0)
+    ctx.set_option(ctx.OPT_BIG_TILES, args.big_tiles)
     dA = ctx.csr_from_scipy(A)
     # device-to-device copy bandwidth on this box (the roofline denominator's cross-check)
     a = ctx.dense_alloc(1 << 22, 64)
