@@ -113,6 +113,12 @@ class ArrowEngine:
             return
         if mode == "fused" and not self.fused_ok:
             raise ValueError("fused mode is not valid for this decomposition")
+        if hasattr(self, "_slots"):                 # streaming slots hold level-0 tiles of the old mode
+            self.stream_drain()
+            for b in self._slots[1]:
+                b.free()
+            self.levels[0].bufs = list(self._slots[0])
+            del self._slots
         for st in self.levels:
             for b in st.bufs:
                 if b is not None:
