@@ -101,6 +101,7 @@ struct arrow_ctx {
     int l2_hints_plain = 3;           // arrow_set_option(ARROW_OPT_L2_HINTS_PLAIN)
     int l2_hints_fused = 0;           // arrow_set_option(ARROW_OPT_L2_HINTS_FUSED)
     int big_tiles = 1;                // arrow_set_option(ARROW_OPT_BIG_TILES): 128-row tiles when k <= 32
+    int spmm_ctas_per_sm = 0;         // arrow_set_option(ARROW_OPT_SPMM_CTAS_PER_SM): 0 = as many as fit
     float *long_scratch = nullptr;    // [slots][k] partial sums of long-row segments
     size_t long_scratch_bytes = 0;
     void *flush_buf = nullptr;
@@ -1054,7 +1055,8 @@ int launch_tiles_gv(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc) {
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TILE_THREADS, SMEM) != cudaSuccess || occ < 1) occ = 1; \
             attr_set = true;                                                                          \
         }                                                                                             \
-        int grid = (int)std::min<long long>((long long)occ * ctx->sm_count, t.n_tiles);               \
+        const int per_sm = (ctx->spmm_ctas_per_sm > 0) ? std::min(occ, ctx->spmm_ctas_per_sm) : occ;   \
+        int grid = (int)std::min<long long>((long long)per_sm * ctx->sm_count, t.n_tiles);            \
         fn<<<grid, TILE_THREADS, SMEM, ctx->stream>>>(t);                                             \
     } while (0)
     if (rowmap && acc) LAUNCH_TL((k_spmm_tiles<G, VPL, true, true, TR, TN>));
@@ -1227,6 +1229,7 @@ int arrow_set_option(arrow_ctx *ctx, int option, int value) {
         case ARROW_OPT_L2_HINTS_PLAIN: ctx->l2_hints_plain = value & 3; return ARROW_OK;
         case ARROW_OPT_L2_HINTS_FUSED: ctx->l2_hints_fused = value & 3; return ARROW_OK;
         case ARROW_OPT_BIG_TILES: ctx->big_tiles = value ? 1 : 0; return ARROW_OK;
+        case ARROW_OPT_SPMM_CTAS_PER_SM: ctx->spmm_ctas_per_sm = value < 0 ? 0 : value; return ARROW_OK;
         default: return fail(ctx, ARROW_ERR_ARG, "unknown option %d", option);
     }
 }

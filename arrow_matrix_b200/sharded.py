@@ -164,6 +164,7 @@ class ShardedArrowEngine:
     def __init__(self, plan: ShardPlan, k: int, backend, overlap: bool = False):
         self.plan, self.k, self.be = plan, int(k), backend
         self.overlap = bool(overlap) and hasattr(backend, "side_begin")
+        self.overlap_ctas = 3
         self.rank, self.world, self.width, self.L = plan.rank, plan.world, plan.width, plan.L
         self.mode = "exchange-" + type(backend).__name__
         be = backend
@@ -349,7 +350,9 @@ class ShardedArrowEngine:
             self.xi[j] = self.ci[j]
             be.barrier(side=True)
         be.bcast_head((0, self.xi[0]), min(self.width, pl.levels[0].rows_global))
+        be.limit_spmm(self.overlap_ctas)        # leave SM resources to the exchange kernels on the side lane
         self._spmm_one(0)
+        be.limit_spmm(0)
         be.side_join()
         for j in range(1, self.L):
             be.bcast_head((j, self.xi[j]), min(self.width, pl.levels[j].rows_global))
@@ -478,6 +481,9 @@ class CudaPeerBackend:
             self.ctx.set_lane(0)
         else:
             self.ctx.peer_barrier(self._flags, self.rank)
+
+    def limit_spmm(self, ctas_per_sm: int):
+        self.ctx.set_option(self.ctx.OPT_SPMM_CTAS_PER_SM, ctas_per_sm)
 
     def side_begin(self):
         """the side lane waits for everything issued so far on the main lane"""

@@ -54,6 +54,9 @@ class GlooNumpyBackend:
     def side_begin(self):
         pass
 
+    def limit_spmm(self, n):
+        pass
+
     def side_join(self):
         pass
 
