@@ -360,6 +360,29 @@ class ShardedArrowEngine:
         self.aggregate()
 
     # -- accounting ----------------------------------------------------------------------------------------------
+    def time_level_spmm(self, j: int, iters: int, warmup: int = 3) -> float:
+        """Average duration (ms) of this rank's level-``j`` SpMM launch alone (CUDA events on its stream)."""
+        ctx = self.be.ctx
+        sh = self.plan.levels[j]
+        if self.mats[j] is None or sh.local_rows == 0:
+            return 0.0
+        src = self.tiles[j][self.xi[j]]
+        scratch = ctx.dense_alloc(sh.local_rows, self.k)
+        for _ in range(warmup):
+            ctx.spmm(self.mats[j], src, scratch)
+        ctx.timer_start(5)
+        for _ in range(iters):
+            ctx.spmm(self.mats[j], src, scratch)
+        ctx.timer_stop(5)
+        ms = ctx.timer_ms(5) / iters
+        scratch.free()
+        return ms
+
+    def level_bytes(self, j: int) -> float:
+        """algorithmic bytes of this rank's level-``j`` launch"""
+        sh = self.plan.levels[j]
+        return sh.nnz * 8 + (sh.local_rows + 1) * 4 + 2.0 * sh.local_rows * self.k * 4
+
     def flops_per_step(self) -> float:
         return 2.0 * self.total_nnz * self.k
 

@@ -248,7 +248,7 @@ def run_b200(a):
         if kms:
             kb = eng.level_bytes(0)
             roof = {"bound": "hbm", "achieved": kb / kms / 1e6, "peak": peak, "unit": "GB/s", "frac": kb / kms / 1e6 / peak,
-                    "traffic": traffic_from_profile(a), "kernel": "k_spmm_* level 0 (one launch)", "kernel_ms": kms,
+                    "traffic": traffic_from_profile(a), "kernel": "k_spmm_tiles level 0 (one launch%s)" % ("" if world == 1 else ", rank 0's shard"), "kernel_ms": kms,
                     "algorithmic_bytes_per_launch": kb, "peak_source": peak_src}
 
     # ---- end to end through the public classes with host buffers --------------------------------------------
