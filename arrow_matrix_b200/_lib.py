@@ -184,7 +184,7 @@ class Context:
     def set_tuning(self, long_row_threshold: int, long_row_segment: int):
         self._check(self.lib.arrow_set_tuning(self._h, int(long_row_threshold), int(long_row_segment)))
 
-    OPT_L2_HINTS_PLAIN, OPT_L2_HINTS_FUSED, OPT_BIG_TILES, OPT_SPMM_CTAS_PER_SM = 1, 2, 3, 4
+    OPT_L2_HINTS_PLAIN, OPT_L2_HINTS_FUSED, OPT_BIG_TILES, OPT_SPMM_CTAS_PER_SM, OPT_PREFETCH = 1, 2, 3, 4, 5
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.arrow_set_option(self._h, int(option), int(value)))

@@ -102,6 +102,7 @@ struct arrow_ctx {
     int l2_hints_fused = 0;           // arrow_set_option(ARROW_OPT_L2_HINTS_FUSED)
     int big_tiles = 1;                // arrow_set_option(ARROW_OPT_BIG_TILES): 128-row tiles when k <= 32
     int spmm_ctas_per_sm = 0;         // arrow_set_option(ARROW_OPT_SPMM_CTAS_PER_SM): 0 = as many as fit
+    int prefetch_mask = 0;            // arrow_set_option(ARROW_OPT_PREFETCH): bit 0 plain launches, bit 1 fused launches
     float *long_scratch = nullptr;    // [slots][k] partial sums of long-row segments
     size_t long_scratch_bytes = 0;
     void *flush_buf = nullptr;
@@ -598,6 +599,7 @@ struct TileArgs {
     int skip;            // indices may hold -1
     int *ticket;         // dynamic tile scheduler (zeroed before the launch)
     int l2_hints;        // bit 0: X gathers evict_last, bit 1: CSR / C streams evict_first
+    int prefetch;        // 1: prefetch.global.L2 the X rows of the group's next row while the current one is computed
 };
 
 template <int G, int VPL, bool ROWMAP, bool ACC, int TR, int TN>
@@ -679,6 +681,25 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
             if (ROWMAP) {
                 orow = __ldg(a.rowmap + row);
                 if (orow < 0) continue;
+            }
+            if (t.prefetch) {
+                // software prefetch into L2: the X rows the group's NEXT row of this tile will gather (their column
+                // indices are already in shared memory); hides DRAM latency of first-touch / scattered rows
+                const int nlr = lr + (TILE_THREADS / 32) * RPW;
+                if (nlr < n_rows_tile) {
+                    const int ns = s_ptr[nlr], ne = s_ptr[nlr + 1];
+                    if (ne - ns <= a.long_threshold) {
+                        const int lines = (a.k * 4 + 127) >> 7;
+                        for (int q = ns + gl; q < ne; q += G) {
+                            const int cq = s_idx[q];
+                            if (cq >= 0) {
+                                const char *xr = reinterpret_cast<const char *>(a.X) + (long long)cq * a.k * 4;
+                                for (int l = 0; l < lines; ++l)
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + l * 128));
+                            }
+                        }
+                    }
+                }
             }
             // accumulate mode: the old C row is read FIRST so that its latency hides behind the gathers (only this
             // group ever touches the row: the row maps are injective)
@@ -1230,6 +1251,7 @@ int arrow_set_option(arrow_ctx *ctx, int option, int value) {
         case ARROW_OPT_L2_HINTS_FUSED: ctx->l2_hints_fused = value & 3; return ARROW_OK;
         case ARROW_OPT_BIG_TILES: ctx->big_tiles = value ? 1 : 0; return ARROW_OK;
         case ARROW_OPT_SPMM_CTAS_PER_SM: ctx->spmm_ctas_per_sm = value < 0 ? 0 : value; return ARROW_OK;
+        case ARROW_OPT_PREFETCH: ctx->prefetch_mask = value & 3; return ARROW_OK;
         default: return fail(ctx, ARROW_ERR_ARG, "unknown option %d", option);
     }
 }
@@ -1725,6 +1747,7 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
             t.skip = A->may_skip ? 1 : 0;
             t.ticket = ctx->tile_ticket;
             t.l2_hints = (rm != nullptr || acc) ? ctx->l2_hints_fused : ctx->l2_hints_plain;
+            t.prefetch = ((rm != nullptr || acc) ? (ctx->prefetch_mask >> 1) : ctx->prefetch_mask) & 1;
             int rc = launch_tiles(ctx, t, A, rm != nullptr, acc, vpl_req);
             if (rc != ARROW_OK) return rc;
         }

@@ -46,6 +46,7 @@ def parse():
                     help="multi-GPU level exchange: NVLink peer pulls (default) or NCCL all-to-all")
     ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the forward exchange with the level-0 SpMM (1/0)")
     ap.add_argument("--l2-hints", type=str, default="", help="plain,fused L2 hint masks of the tile kernel (e.g. 3,0)")
+    ap.add_argument("--prefetch", type=int, default=-1, help="tile kernel L2 prefetch mask (bit0 plain, bit1 fused); -1 = library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-blocks", type=int, default=0)
@@ -200,6 +201,8 @@ def run_b200(a):
         hp, hf = (int(x) for x in a.l2_hints.split(","))
         ctx.set_option(ctx.OPT_L2_HINTS_PLAIN, hp)
         ctx.set_option(ctx.OPT_L2_HINTS_FUSED, hf)
+    if a.prefetch >= 0:
+        ctx.set_option(ctx.OPT_PREFETCH, a.prefetch)
     rows_local = eng.local_rows if hasattr(eng, "local_rows") else eng.levels[0].rows
     rng = np.random.default_rng(42 + rank)
     hostX = _lib.PinnedArray((rows_local, a.k))

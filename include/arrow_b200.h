@@ -68,6 +68,7 @@ int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segme
 #define ARROW_OPT_L2_HINTS_PLAIN 1
 #define ARROW_OPT_L2_HINTS_FUSED 2
 #define ARROW_OPT_BIG_TILES      3   /* 1 (default): 128-row / 2048-entry CSR tiles when k <= 32 */
+#define ARROW_OPT_PREFETCH        5   /* software L2 prefetch of the next row's X lines: bit 0 = plain launches, bit 1 = fused */
 #define ARROW_OPT_SPMM_CTAS_PER_SM 4 /* cap on resident SpMM CTAs per SM (0 = no cap): leaves SM resources to exchange
                                         kernels running on the side lane */
 int  arrow_set_option(arrow_ctx *ctx, int option, int value);
