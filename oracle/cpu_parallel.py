@@ -44,7 +44,9 @@ class CpuArrowReference:
         self.lib = _o._lib()
         self.k, self.width = k, width
         self.P = n_threads or (os.cpu_count() or 1)
-        self.pool = ThreadPoolExecutor(max_workers=self.P)
+        self._cpus = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(self.P))
+        self._next_cpu = [0]
+        self.pool = ThreadPoolExecutor(max_workers=self.P, initializer=self._pin)
         self.L = len(decomposition)
         self.n_blocks = [_o.number_of_blocks(B, width) for B, _ in decomposition]
         _, self.to_prev, _, _ = _o.prepare_permutations([p for _, p in decomposition], self.n_blocks, width)
@@ -59,20 +61,45 @@ class CpuArrowReference:
             self.levels.append(dict(indptr=np.ascontiguousarray(B.indptr[:rows + 1], dtype=np.int32), indices=idx,
                                     data=np.ascontiguousarray(B.data[:nnz], dtype=np.float32), nnz=nnz))
         self.maps = [None] + [np.ascontiguousarray(self.to_prev[j][: self.rows[j]], dtype=np.int64) for j in range(1, self.L)]
-        self.X = [np.zeros((r, k), np.float32) for r in self.rows]
-        self.C = [np.zeros((r, k), np.float32) for r in self.rows]
         nt = self.P * tasks_per_thread
         self.spmm_ranges = [_nnz_balanced_ranges(lv["indptr"], nt) for lv in self.levels]
         self.row_ranges = [[(int(a), int(b)) for a, b in zip(np.linspace(0, r, nt + 1)[:-1].astype(np.int64),
                                                              np.linspace(0, r, nt + 1)[1:].astype(np.int64)) if b > a]
                            for r in self.rows]
         self.total_nnz = sum(lv["nnz"] for lv in self.levels)
+        self.X = [np.empty((r, k), np.float32) for r in self.rows]
+        self.C = [np.empty((r, k), np.float32) for r in self.rows]
+        for j in range(self.L):
+            self._first_touch(self.X[j], self.spmm_ranges[j])
+            self._first_touch(self.C[j], self.spmm_ranges[j])
+
+    def _pin(self):
+        """one worker thread per core, like one MPI rank per core (sched_setaffinity(0, ...) acts on the calling thread)"""
+        try:
+            i = self._next_cpu[0]
+            self._next_cpu[0] += 1
+            os.sched_setaffinity(0, {self._cpus[i % len(self._cpus)]})
+        except Exception:
+            pass
 
     def _run(self, fn, tasks):
         list(self.pool.map(fn, tasks))
 
+    def _first_touch(self, arr, ranges):
+        """pages are placed on the NUMA node of the thread that first writes them: let each worker zero the row
+        ranges it will later compute, the way every MPI rank of the reference allocates its own tiles"""
+        k = arr.shape[1]
+        lib, P_, i64 = self.lib, ctypes.c_void_p, ctypes.c_int64
+        self._run(lambda rg: lib.oracle_zero_rows_f32(i64(rg[0]), i64(rg[1]), i64(k), P_(arr.ctypes.data)), ranges)
+
     def set_features(self, X0: np.ndarray):
-        self.X[0] = np.ascontiguousarray(X0, dtype=np.float32)
+        """copy into the NUMA-placed level-0 tile (parallel, by row ranges)"""
+        X0 = np.ascontiguousarray(X0, dtype=np.float32)
+        dst = self.X[0]
+
+        def cp(rg):
+            dst[rg[0]:rg[1]] = X0[rg[0]:rg[1]]
+        self._run(cp, self.spmm_ranges[0])
 
     def step(self) -> np.ndarray:
         lib, k, P_ = self.lib, self.k, ctypes.c_void_p
