@@ -18,7 +18,6 @@ from __future__ import annotations
 import ctypes
 import os
 import time
-from concurrent.futures import ThreadPoolExecutor
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -45,8 +44,17 @@ class CpuArrowReference:
         self.k, self.width = k, width
         self.P = n_threads or (os.cpu_count() or 1)
         self._cpus = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(self.P))
-        self._next_cpu = [0]
-        self.pool = ThreadPoolExecutor(max_workers=self.P, initializer=self._pin)
+        # persistent workers with a STATIC task -> thread map (task i runs on thread i mod P), one thread per core:
+        # the same thread first-touches and later computes a row range, like an MPI rank owning its block-rows
+        import threading
+        self._start = threading.Barrier(self.P + 1)
+        self._done = threading.Barrier(self.P + 1)
+        self._job = None
+        self._stop = False
+        self._errors = []
+        self._threads = [threading.Thread(target=self._worker, args=(t,), daemon=True) for t in range(self.P)]
+        for th in self._threads:
+            th.start()
         self.L = len(decomposition)
         self.n_blocks = [_o.number_of_blocks(B, width) for B, _ in decomposition]
         _, self.to_prev, _, _ = _o.prepare_permutations([p for _, p in decomposition], self.n_blocks, width)
@@ -73,17 +81,29 @@ class CpuArrowReference:
             self._first_touch(self.X[j], self.spmm_ranges[j])
             self._first_touch(self.C[j], self.spmm_ranges[j])
 
-    def _pin(self):
-        """one worker thread per core, like one MPI rank per core (sched_setaffinity(0, ...) acts on the calling thread)"""
+    def _worker(self, t: int):
         try:
-            i = self._next_cpu[0]
-            self._next_cpu[0] += 1
-            os.sched_setaffinity(0, {self._cpus[i % len(self._cpus)]})
+            os.sched_setaffinity(0, {self._cpus[t % len(self._cpus)]})      # acts on the calling thread
         except Exception:
             pass
+        while True:
+            self._start.wait()
+            if self._stop:
+                return
+            fn, tasks = self._job
+            try:
+                for i in range(t, len(tasks), self.P):
+                    fn(tasks[i])
+            except BaseException as e:      # noqa: BLE001
+                self._errors.append(e)
+            self._done.wait()
 
     def _run(self, fn, tasks):
-        list(self.pool.map(fn, tasks))
+        self._job = (fn, tasks)
+        self._start.wait()
+        self._done.wait()
+        if self._errors:
+            raise self._errors.pop()
 
     def _first_touch(self, arr, ranges):
         """pages are placed on the NUMA node of the thread that first writes them: let each worker zero the row
@@ -140,4 +160,8 @@ class CpuArrowReference:
         return 2.0 * self.total_nnz * self.k
 
     def close(self):
-        self.pool.shutdown()
+        if not self._stop:
+            self._stop = True
+            self._start.wait()
+            for th in self._threads:
+                th.join(5)
