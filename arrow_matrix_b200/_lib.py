@@ -29,7 +29,7 @@ EXPORTS = [
     "arrow_dense_copy", "arrow_dense_ptr", "arrow_dense_wrap", "arrow_host_alloc", "arrow_host_free",
     "arrow_dense_h2d_lane", "arrow_dense_d2h_lane", "arrow_lane_wait", "arrow_lane_sync", "arrow_set_lane",
     "arrow_event_record", "arrow_event_wait",
-    "arrow_spmm", "arrow_gather_rows", "arrow_gather_rows_multi",
+    "arrow_spmm", "arrow_spmm_add", "arrow_gather_rows", "arrow_gather_rows_multi",
     "arrow_ipc_export", "arrow_ipc_import", "arrow_peer_barrier",
     "arrow_timer_start", "arrow_timer_stop", "arrow_timer_elapsed_ms", "arrow_launch_count", "arrow_l2_flush",
 ]
@@ -94,6 +94,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         "arrow_host_alloc": (c_int, [c_size_t, POINTER(P)]),
         "arrow_host_free": (c_int, [P]),
         "arrow_spmm": (c_int, [P, I, I, I, I, I, I]),
+        "arrow_spmm_add": (c_int, [P, I, I, I, I, I, I]),
         "arrow_gather_rows": (c_int, [P, I, I, I, I]),
         "arrow_gather_rows_multi": (c_int, [P, I, pI, pI64, I, I, I]),
         "arrow_ipc_export": (c_int, [P, I, P]),
@@ -253,6 +254,10 @@ class Context:
              accumulate: bool = False, variant: int = VARIANT_AUTO):
         self._check(self.lib.arrow_spmm(self._h, A.h, X.h, C.h, rowmap.h if rowmap is not None else -1,
                                         ACCUMULATE if accumulate else 0, int(variant)))
+
+    def spmm_add(self, A: "Csr", X: "Dense", C: "Dense", add: "Dense", add_map: "RowMap", variant: int = VARIANT_AUTO):
+        """C[r] = (A X)[r] + add[add_map[r]] (where add_map[r] >= 0)"""
+        self._check(self.lib.arrow_spmm_add(self._h, A.h, X.h, C.h, add.h, add_map.h, int(variant)))
 
     def gather_rows(self, dst: "Dense", src: "Dense", m: "RowMap", accumulate: bool = False):
         self._check(self.lib.arrow_gather_rows(self._h, dst.h, src.h, m.h, ACCUMULATE if accumulate else 0))

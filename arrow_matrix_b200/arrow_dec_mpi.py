@@ -97,7 +97,8 @@ class ArrowDecompositionMPI:
             self._engine = ShardedArrowEngine(plan, self._n_feature_columns, be)
         else:
             self._engine = ArrowEngine(blocks.decomposition, blocks.width, self._n_feature_columns,
-                                       block_diagonal=blocks.block_diagonal, mode=self._mode, n_blocks=self.n_blocks)
+                                       block_diagonal=blocks.block_diagonal, mode=self._mode, n_blocks=self.n_blocks,
+                                       fused_style=getattr(self, "_fused_style", "gather"))
         self.decomposition_length = self._engine.L
 
     def load_data_from_blocks(self, blocked: DecompositionBlocks):

@@ -200,6 +200,8 @@ struct SpmmArgs {
     int k;                            // feature columns
     int k4;                           // k / 4 (vector kernels)
     int long_threshold;               // rows with more entries are left to the long-row kernels
+    const float *__restrict__ add_src;   // optional addend: C[r] = sum + add_src[add_map[r]] (add_map[r] >= 0), else nullptr
+    const int *__restrict__ add_map;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -708,6 +710,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
 #pragma unroll
             for (int i = 0; i < VPL; ++i)
                 acc[i] = (ACC && gl + i * G < k4) ? ld_f4_hint(cr + i * G, pol_stream) : f4_zero();
+            if (a.add_map != nullptr) {
+                // epilogue gather-add, issued first so its latency hides behind the gathers: the backward exchange
+                // C_{j-1}[to_prev[r]] += C_j[r] (arrow_dec_mpi.py:437) seen from the receiving row
+                const int am = __ldg(a.add_map + row);
+                if (am >= 0) {
+                    const float4 *ar = reinterpret_cast<const float4 *>(a.add_src) + (long long)am * k4 + gl;
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i)
+                        if (gl + i * G < k4) f4_add(acc[i], ld_f4_hint(ar + i * G, pol_stream));
+                }
+            }
             int p = s;
             if (EXACT && !t.skip) {
                 // unpredicated batches: full UNROLL batches, then the remainder as 4 / 2 / 1 (binary decomposition) --
@@ -801,12 +814,15 @@ __global__ void __launch_bounds__(256) k_spmm_generic(SpmmArgs a) {
                     if (col < a.k) acc[i] = fmaf(v, __ldg(xr + col), acc[i]);
                 }
             }
+            const int am = (a.add_map != nullptr) ? __ldg(a.add_map + row) : -1;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int col = c0 + lane + 32 * i;
                 if (col < a.k) {
                     float *dst = a.C + orow * a.k + col;
-                    *dst = ACC ? (*dst + acc[i]) : acc[i];
+                    float r = ACC ? (*dst + acc[i]) : acc[i];
+                    if (am >= 0) r += a.add_src[(long long)am * a.k + col];
+                    *dst = r;
                 }
             }
         }
@@ -861,7 +877,8 @@ template <bool ROWMAP, bool ACC>
 __global__ void __launch_bounds__(128) k_spmm_long_reduce(const int *__restrict__ long_rows,
                                                           const int *__restrict__ long_first,
                                                           const float *__restrict__ scratch,
-                                                          float *__restrict__ C, const int *__restrict__ rowmap, int k) {
+                                                          float *__restrict__ C, const int *__restrict__ rowmap, int k,
+                                                          const float *__restrict__ add_src, const int *__restrict__ add_map) {
     const int r = long_rows[blockIdx.x];
     long long orow = r;
     if (ROWMAP) {
@@ -872,6 +889,10 @@ __global__ void __launch_bounds__(128) k_spmm_long_reduce(const int *__restrict_
     for (int col = threadIdx.x; col < k; col += blockDim.x) {
         float sum = 0.f;
         for (int s = s0; s < s1; ++s) sum += scratch[(long long)s * k + col];
+        if (add_map != nullptr) {
+            const int am = add_map[r];
+            if (am >= 0) sum += add_src[(long long)am * k + col];
+        }
         float *dst = C + orow * k + col;
         *dst = ACC ? (*dst + sum) : sum;
     }
@@ -1684,7 +1705,17 @@ int arrow_host_free(void *ptr) {
 }
 
 // ---- hot path -----------------------------------------------------------------------------------
+static int spmm_impl(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int flags, int variant, int add_buf, int add_map);
+
 int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int flags, int variant) {
+    return spmm_impl(ctx, csr, x_buf, c_buf, rowmap, flags, variant, -1, -1);
+}
+
+int arrow_spmm_add(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int add_buf, int add_map, int variant) {
+    return spmm_impl(ctx, csr, x_buf, c_buf, -1, 0, variant, add_buf, add_map);
+}
+
+static int spmm_impl(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int flags, int variant, int add_buf, int add_map) {
     CHECK_CTX(ctx);
     Csr *A = get_csr(ctx, csr);
     DenseBuf *X = get_dense(ctx, x_buf), *C = get_dense(ctx, c_buf);
@@ -1716,9 +1747,23 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
     a.k = k;
     a.k4 = k / 4;
     a.long_threshold = A->long_threshold;
+    a.add_src = nullptr;
+    a.add_map = nullptr;
+    if (add_buf >= 0 || add_map >= 0) {
+        DenseBuf *S = get_dense(ctx, add_buf);
+        IdxMap *am = get_map(ctx, add_map);
+        if (!S || !am) return fail(ctx, ARROW_ERR_HANDLE, "bad addend handles (buf=%d map=%d)", add_buf, add_map);
+        if (S->k != k) return fail(ctx, ARROW_ERR_ARG, "addend has %d feature columns, expected %d", S->k, k);
+        if (am->n < A->n_rows) return fail(ctx, ARROW_ERR_ARG, "addend map has %lld entries, block has %lld rows", (long long)am->n, (long long)A->n_rows);
+        if (am->limit > S->rows) return fail(ctx, ARROW_ERR_ARG, "addend map reaches row %lld, addend tile has %lld rows", (long long)am->limit, (long long)S->rows);
+        if (S->p == C->p) return fail(ctx, ARROW_ERR_ARG, "addend and C must not alias");
+        a.add_src = S->p;
+        a.add_map = am->p;
+    }
     if (variant == ARROW_VARIANT_AUTO) variant = pick_variant(k);
     const int vpl_req = (variant >> 4) & 0xF;          // optional float4-per-lane override (tile kernel)
     variant &= 0xF;
+    if (a.add_map != nullptr && variant != 3) variant = 3;   // the epilogue gather-add lives in the tile / generic / long kernels
     if (variant < 0 || variant > 3) return fail(ctx, ARROW_ERR_ARG, "unknown variant %d", variant);
 
     const bool vec_ok = (k % 4 == 0) && k <= 256;
@@ -1790,10 +1835,10 @@ int arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int fl
         k_spmm_long_partial<<<A->n_long_tasks, 256, smem, ctx->stream>>>(la);
         ctx->launches++;
         const int *rmp = rm ? rm->p : nullptr;
-        if (rm && acc) k_spmm_long_reduce<true, true><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
-        else if (rm) k_spmm_long_reduce<true, false><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
-        else if (acc) k_spmm_long_reduce<false, true><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
-        else k_spmm_long_reduce<false, false><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k);
+        if (rm && acc) k_spmm_long_reduce<true, true><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k, a.add_src, a.add_map);
+        else if (rm) k_spmm_long_reduce<true, false><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k, a.add_src, a.add_map);
+        else if (acc) k_spmm_long_reduce<false, true><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k, a.add_src, a.add_map);
+        else k_spmm_long_reduce<false, false><<<A->n_long_rows, 128, 0, ctx->stream>>>(A->long_rows, A->long_first, ctx->long_scratch, C->p, rmp, k, a.add_src, a.add_map);
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
     }

@@ -30,7 +30,7 @@ from . import decomp
 
 class _LevelState:
     __slots__ = ("rows", "n_blocks", "csr", "csr_fused", "to_prev", "to_next_dev", "to_prev_dev", "cmap_dev",
-                 "bufs", "xi", "ci", "nnz", "dropped")
+                 "bufs", "xi", "ci", "nnz", "dropped", "cbuf")
 
     def __init__(self):
         self.csr = self.csr_fused = None
@@ -38,6 +38,7 @@ class _LevelState:
         self.to_prev_dev = self.to_next_dev = self.cmap_dev = None
         self.bufs = [None, None]
         self.xi = self.ci = 0
+        self.cbuf = None
 
 
 class ArrowEngine:
@@ -46,11 +47,14 @@ class ArrowEngine:
     def __init__(self, decomposition: Sequence[Tuple[decomp.Level, np.ndarray]], width: int, k: int,
                  block_diagonal: bool = True, device: int = 0, mode: str = "auto", stream: Optional[int] = None,
                  variant: int = _lib.VARIANT_AUTO, n_blocks: Optional[Sequence[int]] = None,
-                 ctx: Optional[_lib.Context] = None):
+                 ctx: Optional[_lib.Context] = None, fused_style: str = "gather"):
         if mode not in ("auto", "fused", "exchange"):
             raise ValueError(f"mode must be auto|fused|exchange, got {mode!r}")
         self.ctx = ctx if ctx is not None else _lib.Context(device, stream)
         self.width, self.k, self.variant = int(width), int(k), variant
+        if fused_style not in ("gather", "scatter"):
+            raise ValueError("fused_style must be 'gather' or 'scatter'")
+        self.fused_style = fused_style
         self.block_diagonal = block_diagonal
         self.L = len(decomposition)
         if self.L == 0:
@@ -106,6 +110,8 @@ class ArrowEngine:
                 st.xi, st.ci = 0, 0             # zero_rhs: X and C both zero (arrow_slim_mpi.py:354-394)
             if j > 0 and self.mode == "fused":
                 st.csr_fused = st.csr.remap_columns(st.cmap_dev, self.levels[0].rows)
+                if self.fused_style == "gather":
+                    st.cbuf = self.ctx.dense_alloc(st.rows, self.k)     # this level's result tile, written once per step
 
     def set_mode(self, mode: str):
         """Switch between 'fused' and 'exchange' (re-allocates level tiles; features are reset)."""
@@ -127,6 +133,9 @@ class ArrowEngine:
             if st.csr_fused is not None:
                 st.csr_fused.free()
                 st.csr_fused = None
+            if st.cbuf is not None:
+                st.cbuf.free()
+                st.cbuf = None
         self.mode = mode
         self._alloc_buffers()
 
@@ -226,11 +235,28 @@ class ArrowEngine:
         """Every level's arrow product (``B.spmm``, arrow_slim_mpi.py:246-280 + :78-155)."""
         if self.mode == "fused":
             st0 = self.levels[0]
+            x = st0.bufs[st0.xi]
             out = 1 - st0.xi
-            self.ctx.spmm(st0.csr, st0.bufs[st0.xi], st0.bufs[out], variant=self.variant)
-            for st in self.levels[1:]:
-                self.ctx.spmm(st.csr_fused, st0.bufs[st0.xi], st0.bufs[out], rowmap=st.cmap_dev, accumulate=True,
-                              variant=self.variant)
+            if self.fused_style == "gather":
+                # deepest level first; every level writes its tile once and ADDS the deeper level's rows that map onto
+                # its own (C_j[r] += C_{j+1}[to_next_j[r]]): the reference's backward aggregation as an epilogue gather
+                for j in range(self.L - 1, 0, -1):
+                    st = self.levels[j]
+                    if j == self.L - 1:
+                        self.ctx.spmm(st.csr_fused, x, st.cbuf, variant=self.variant)
+                    else:
+                        nxt = self.levels[j + 1]
+                        self.ctx.spmm_add(st.csr_fused, x, st.cbuf, nxt.cbuf, nxt.to_next_dev, variant=self.variant)
+                if self.L > 1:
+                    nxt = self.levels[1]
+                    self.ctx.spmm_add(st0.csr, x, st0.bufs[out], nxt.cbuf, nxt.to_next_dev, variant=self.variant)
+                else:
+                    self.ctx.spmm(st0.csr, x, st0.bufs[out], variant=self.variant)
+            else:
+                self.ctx.spmm(st0.csr, x, st0.bufs[out], variant=self.variant)
+                for st in self.levels[1:]:
+                    self.ctx.spmm(st.csr_fused, x, st0.bufs[out], rowmap=st.cmap_dev, accumulate=True,
+                                  variant=self.variant)
             st0.ci = out
             return
         for st in self.levels:

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--overlap", type=int, default=1, help="multi-GPU: overlap the forward exchange with the level-0 SpMM (1/0)")
     ap.add_argument("--l2-hints", type=str, default="", help="plain,fused L2 hint masks of the tile kernel (e.g. 3,0)")
     ap.add_argument("--prefetch", type=int, default=-1, help="tile kernel L2 prefetch mask (bit0 plain, bit1 fused); -1 = library default")
+    ap.add_argument("--fused-style", type=str, default="gather", choices=["gather", "scatter"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-blocks", type=int, default=0)
@@ -193,6 +194,7 @@ def run_b200(a):
         del dec
         blocks, n_blocks, to_prev, to_next = ArrowDecompositionMPI.load_decomposition_new(comm, base, a.width, True, slim=True)
         arrow = ArrowDecompositionMPI.initialize(comm, n_blocks, to_prev, to_next, a.width, a.k, 'gpu', True, True, mode=a.mode)
+        arrow._fused_style = a.fused_style
         arrow.B.load_sparse_matrix_from_blocks(blocks)
         arrow.B.zero_rhs(a.width, a.k)
         eng = arrow._engine
@@ -325,7 +327,7 @@ def run_b200(a):
         line = {"metric": "iterated SpMM GFLOP/s (k=%d)" % a.k, "value": flops / ms_step / 1e6, "unit": "GFLOP/s",
                 "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(a), "mode": eng.mode, "overlap": bool(getattr(eng, "overlap", False)), "l2": "inputs larger than L2 (features 5.12 GB per pass at the default size); no flush",
+                "config": {"workload": workload_name(a), "mode": eng.mode + ("/" + eng.fused_style if getattr(eng, "fused_style", None) and eng.mode == "fused" else ""), "overlap": bool(getattr(eng, "overlap", False)), "l2": "inputs larger than L2 (features 5.12 GB per pass at the default size); no flush",
                            "total_nnz": int(eng.total_nnz), "setup_s": round(t_setup, 1)},
                 "hbm_gbs_effective": alg_bytes / ms_step / 1e6, "algorithmic_bytes_per_step": alg_bytes,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}

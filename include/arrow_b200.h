@@ -142,6 +142,11 @@ int  arrow_host_free(void *ptr);
  * X must have >= n_cols rows; C must cover every out(r); X and C must not alias. */
 int  arrow_spmm(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int rowmap, int flags, int variant);
 
+/* C[r, :] = sum_p A[r, col_p] * X[col_p, :] + add[add_map[r], :]   (rows with add_map[r] == -1 get the product only).
+ * The backward exchange C_{j-1}[to_prev[r]] += C_j[r] (arrow_dec_mpi.py:437) folded into the RECEIVING level's SpMM as
+ * a gather-add: levels are multiplied deepest first, each writes its tile once, nothing is read-modify-written. */
+int  arrow_spmm_add(arrow_ctx *ctx, int csr, int x_buf, int c_buf, int add_buf, int add_map, int variant);
+
 /* dst[r, :] (+)= src[map[r], :] for r in [0, map length); rows with map[r] == -1 are left alone
  * (the reference's stale-row behaviour, arrow_dec_mpi.py:544).  Forward exchange with to_prev,
  * backward exchange (as a gather-add) with to_next. */

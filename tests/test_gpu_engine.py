@@ -65,18 +65,23 @@ def test_exchange_mode_level_tiles_and_stale_rows(cuda_device):
     eng.close()
 
 
-def test_fused_equals_exchange_bitwise_inputs(cuda_device):
-    w, t0, k = 100, 10, 32
-    dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=8)
+@pytest.mark.parametrize("levels,k", [(2, 32), (3, 16), (3, 6), (4, 128)])
+def test_fused_styles_equal_exchange(cuda_device, levels, k):
+    """fused/gather (epilogue gather-add), fused/scatter (row-map epilogue) and the literal exchange agree"""
+    w, t0 = 100, 16
+    dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=8, hub_rows=2, hub_nnz=900)
     X = synth.generate_dense_matrix(t0 * w, k, np.float32, np.random.default_rng(0))
     res = {}
-    for mode in ("fused", "exchange"):
-        eng = ArrowEngine(dec, w, k, device=cuda_device, mode=mode)
+    for name, kw in (("gather", dict(mode="fused", fused_style="gather")), ("scatter", dict(mode="fused", fused_style="scatter")),
+                     ("exchange", dict(mode="exchange"))):
+        eng = ArrowEngine(dec, w, k, device=cuda_device, **kw)
         eng.set_features(X)
         eng.step()
-        res[mode] = eng.result()
+        eng.step()                  # chained second iteration
+        res[name] = eng.result()
         eng.close()
-    assert_close(res["fused"], res["exchange"])
+    assert_close(res["gather"], res["exchange"], tol=2e-5)
+    assert_close(res["scatter"], res["exchange"], tol=2e-5)
 
 
 def test_arrow_pattern_masking(cuda_device):

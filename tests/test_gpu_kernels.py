@@ -218,3 +218,29 @@ def test_errors_are_reported(ctx):
         ctx.spmm(A, ctx.dense_alloc(4, 4), ctx.dense_alloc(8, 4))   # X too short
     with pytest.raises(_lib.ArrowError):
         ctx.csr_upload(2, 2, np.array([0, 2, 1]), np.array([0]), None)      # decreasing indptr
+
+
+@pytest.mark.parametrize("k", [16, 128, 6, 256])
+def test_spmm_add_epilogue_gather(ctx, k):
+    """C[r] = (A X)[r] + add[add_map[r]]: the backward exchange folded into the receiving level (incl. long rows)"""
+    rng = np.random.default_rng(17)
+    n, m = 3000, 1300
+    lens = rng.integers(0, 12, size=n)
+    lens[4] = 2000                      # long row: segmented path must apply the addend too
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    cols = np.concatenate([np.sort(rng.choice(n, size=l, replace=False)) for l in lens]).astype(np.int32)
+    A = sparse.csr_matrix((rng.random(cols.size, dtype=np.float32), cols, indptr), shape=(n, n))
+    X = synth.generate_dense_matrix(n, k, np.float32, rng)
+    add = synth.generate_dense_matrix(m, k, np.float32, rng)
+    amap = np.full(n, -1, dtype=np.int64)
+    pick = rng.permutation(n)[:m]
+    amap[pick] = rng.permutation(m)
+    amap[4] = 7
+    dA, dX, dC, dAdd = ctx.csr_from_scipy(A), ctx.dense_from_host(X), ctx.dense_alloc(n, k), ctx.dense_from_host(add)
+    dmap = ctx.map_upload(amap, m)
+    dC.fill(5.0)
+    ctx.spmm_add(dA, dX, dC, dAdd, dmap)
+    ref = ref_spmm64(A, X)
+    ok = amap >= 0
+    ref[ok] += add[amap[ok]]
+    assert_close(dC.d2h(), ref)
