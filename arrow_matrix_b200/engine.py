@@ -336,26 +336,42 @@ class ArrowEngine:
                 total += 5.0 * m * self.k * 4
         return total
 
-    def time_level_spmm(self, j: int, iters: int, warmup: int = 3) -> float:
-        """Average duration (ms) of level ``j``'s plain arrow SpMM launch, CUDA events on the engine's stream."""
+    def _launch_level_as_in_step(self, j: int, src, dst):
         st = self.levels[j]
-        src = self.levels[0].bufs[self.levels[0].xi] if (self.mode == "fused" and j > 0) else st.bufs[st.xi]
+        if self.mode == "fused" and self.fused_style == "gather" and j + 1 < self.L:
+            nxt = self.levels[j + 1]
+            self.ctx.spmm_add(st.csr, src, dst, nxt.cbuf, nxt.to_next_dev, variant=self.variant)
+        else:
+            self.ctx.spmm(st.csr, src, dst, variant=self.variant)
+
+    def time_level_spmm(self, j: int, iters: int, warmup: int = 3) -> float:
+        """Average duration (ms) of level ``j``'s launch exactly as ``step()`` issues it (level 0 of the fused/gather
+        path includes the epilogue gather-add of level 1's tile), CUDA events on the engine's stream."""
+        st = self.levels[j]
         if j > 0 and self.mode == "fused":
-            raise ValueError("levels > 0 have no standalone launch in fused mode")
+            raise ValueError("levels > 0 are timed through step() in fused mode")
+        src = st.bufs[st.xi]
         scratch = self.ctx.dense_alloc(st.rows, self.k)
         for _ in range(warmup):
-            self.ctx.spmm(st.csr, src, scratch, variant=self.variant)
+            self._launch_level_as_in_step(j, src, scratch)
         self.ctx.timer_start(5)
         for _ in range(iters):
-            self.ctx.spmm(st.csr, src, scratch, variant=self.variant)
+            self._launch_level_as_in_step(j, src, scratch)
         self.ctx.timer_stop(5)
         ms = self.ctx.timer_ms(5) / iters
         scratch.free()
         return ms
 
     def level_bytes(self, j: int) -> float:
+        """algorithmic bytes of level ``j``'s launch: nnz*8 + (R+1)*4 + R*k*4 (X) + R*k*4 (C), plus -- when the launch
+        carries the epilogue gather-add -- one read of the routed rows of the deeper level's tile (the other two passes
+        of the reference's backward exchange do not exist in this launch)"""
         st = self.levels[j]
-        return st.nnz * 8 + (st.rows + 1) * 4 + 2.0 * st.rows * self.k * 4
+        b = st.nnz * 8 + (st.rows + 1) * 4 + 2.0 * st.rows * self.k * 4
+        if self.mode == "fused" and self.fused_style == "gather" and j + 1 < self.L:
+            nxt = self.levels[j + 1]
+            b += float(np.count_nonzero(nxt.to_prev < st.rows)) * self.k * 4
+        return b
 
     def close(self):
         self.ctx.close()
