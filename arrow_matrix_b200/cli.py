@@ -35,7 +35,10 @@ def main(argv=None) -> None:
     parser.add_argument('-n', '--npy', type=str2bool, nargs="?", default=True,
                         help='If true, the decomposition is loaded from the indices / indptr files.')
     args = vars(parser.parse_args(argv))
-    print(str(args), flush=True)
+    from . import comm as comm_mod
+    comm_mod.init_from_env()                    # torchrun --nproc-per-node N: one process per GPU
+    if comm_mod.world_comm().Get_rank() == 0:
+        print(str(args), flush=True)
     arrow_bench.bench_spmm(args['path'], args['width'], args['features'], args['iterations'], args['blocked'],
                            args['device'], args['ranksperside'], args['ba_neighbors'], None,
                            slim=args['slim'], npy_format=args['npy'])

@@ -69,6 +69,25 @@ class TorchComm:
         return out
 
 
+def init_from_env() -> None:
+    """Under ``torchrun`` (WORLD_SIZE > 1) bring up torch.distributed: NCCL with one GPU per process when CUDA is
+    there, gloo otherwise.  The reference gets its world from ``mpiexec`` + ``MPI.COMM_WORLD`` instead."""
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if torch.cuda.is_available():
+        local = int(os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0")))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+
+
 def world_comm():
     """TorchComm when torch.distributed is up, else SelfComm."""
     try:
