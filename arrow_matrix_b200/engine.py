@@ -170,7 +170,9 @@ class ArrowEngine:
     def result_buffer(self, level: int = 0) -> _lib.Dense:
         st = self.levels[level]
         if st.bufs[0] is None:
-            raise RuntimeError("level tiles are not materialised in fused mode; use mode='exchange'")
+            if st.cbuf is not None:             # fused/gather keeps every level's aggregated result tile
+                return st.cbuf
+            raise RuntimeError("level tiles are not materialised in fused/scatter mode; use mode='exchange'")
         return st.bufs[st.ci]
 
     def result(self, level: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
