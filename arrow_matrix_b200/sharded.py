@@ -34,14 +34,14 @@ from . import decomp
 class LevelShard:
     """Rank-local view of one level."""
     __slots__ = ("level", "n_blocks", "rows_global", "bounds", "r0", "r1", "own_rows", "hoff", "local_rows",
-                 "indptr", "indices", "data", "nnz", "dropped", "fwd_map", "bwd_map")
+                 "indptr", "indices", "data", "nnz", "dropped", "fwd_map", "bwd_map",
+                 "halo_prev_off", "halo_next_off", "halo_prev_src", "halo_next_src")
 
 
 class ShardPlan:
     def __init__(self, decomposition: Sequence[Tuple[decomp.Level, np.ndarray]], width: int, rank: int, world: int,
                  block_diagonal: bool = True, n_blocks: Optional[Sequence[int]] = None):
-        if not block_diagonal:
-            raise NotImplementedError("sharded execution covers the block-diagonal layout (the reference's slim mode)")
+        self.block_diagonal = bool(block_diagonal)
         self.width, self.rank, self.world = int(width), int(rank), int(world)
         self.L = len(decomposition)
         self.n_blocks = [decomp.number_of_blocks(B, width) for B, _ in decomposition] if n_blocks is None \
@@ -57,8 +57,7 @@ class ShardPlan:
             sh.bounds = decomp.block_partition(nb, world) * w                 # global row bounds per rank
             sh.r0, sh.r1 = int(sh.bounds[rank]), int(sh.bounds[rank + 1])
             sh.own_rows = sh.r1 - sh.r0
-            sh.hoff = w if rank > 0 else 0                                    # own rows sit behind the head tile
-            sh.local_rows = sh.hoff + sh.own_rows
+            self._layout(sh, rank)
             self._build_local_matrix(sh, B, nb)
             # exchange maps hold GLOBAL rows of the neighbouring level (or -1)
             sh.fwd_map = sh.bwd_map = None
@@ -72,6 +71,60 @@ class ShardPlan:
                 sh.bwd_map = tn
             self.levels.append(sh)
 
+    # local tile layout of a rank at a level: [head tile (ranks > 0)] [halo: previous block] [own rows] [halo: next block]
+    # The halos exist only in the banded layout (blocks A_i,i-1 / A_i,i+1, arrow_mpi.py:211-219) at shard boundaries.
+    def _halo_flags(self, level_bounds: np.ndarray, nb: int, g: int):
+        w = self.width
+        b0, b1 = int(level_bounds[g]) // w, int(level_bounds[g + 1]) // w
+        if self.block_diagonal or b1 <= b0:
+            return False, False
+        return (b0 >= 2), (b1 < nb)
+
+    def hoff_of(self, level: int, g: int) -> int:
+        """offset of rank ``g``'s own rows inside its local tile of ``level``"""
+        sh = self.levels[level] if level < len(self.levels) else None
+        bounds = sh.bounds if sh is not None else None
+        nb = self.n_blocks[level]
+        if bounds is None:
+            bounds = decomp.block_partition(nb, self.world) * self.width
+        prev, _ = self._halo_flags(bounds, nb, g)
+        return (self.width if g > 0 else 0) + (self.width if prev else 0)
+
+    def _layout(self, sh: LevelShard, rank: int):
+        w = self.width
+        prev, nxt = self._halo_flags(sh.bounds, sh.n_blocks, rank)
+        head = w if rank > 0 else 0
+        sh.halo_prev_off = head if prev else -1
+        sh.hoff = head + (w if prev else 0)
+        sh.halo_next_off = sh.hoff + sh.own_rows if nxt else -1
+        sh.local_rows = sh.hoff + sh.own_rows + (w if nxt else 0)
+        # where the halo rows live: (owner rank, global first row)
+        sh.halo_prev_src = sh.halo_next_src = None
+        if prev:
+            g0 = sh.r0 - w
+            sh.halo_prev_src = (int(np.searchsorted(sh.bounds, g0, side="right") - 1), g0)
+        if nxt:
+            g1 = sh.r1
+            sh.halo_next_src = (int(np.searchsorted(sh.bounds, g1, side="right") - 1), g1)
+
+    def _local_cols(self, sh: LevelShard, idx: np.ndarray) -> np.ndarray:
+        """global column -> local column of this rank's tile (-1 if the column is not held locally)"""
+        w, rank = self.width, self.rank
+        out = np.full(idx.shape, -1, dtype=np.int64)
+        own = (idx >= sh.r0) & (idx < sh.r1)
+        out[own] = idx[own] - sh.r0 + sh.hoff
+        if rank > 0:
+            head = idx < w
+            out[head] = idx[head]
+        if sh.halo_prev_off >= 0:
+            lo = sh.r0 - w
+            m = (idx >= lo) & (idx < sh.r0)
+            out[m] = idx[m] - lo + sh.halo_prev_off
+        if sh.halo_next_off >= 0:
+            m = (idx >= sh.r1) & (idx < sh.r1 + w)
+            out[m] = idx[m] - sh.r1 + sh.halo_next_off
+        return out
+
     def _build_local_matrix(self, sh: LevelShard, B, nb: int):
         w, rank = self.width, self.rank
         parts_ptr, parts_idx, parts_dat = [], [], []
@@ -79,7 +132,7 @@ class ShardPlan:
         has_data = decomp.level_triplet(B)[0] is not None
         if rank > 0:
             # partial head rows: rows [0, w) of the level restricted to this rank's columns
-            ip, idx, dat, d0 = decomp.arrow_rows(B, w, nb, True, 0, min(w, sh.rows_global))
+            ip, idx, dat, d0 = decomp.arrow_rows(B, w, nb, self.block_diagonal, 0, min(w, sh.rows_global))
             dropped += d0 if rank == 0 else 0
             keep = (idx >= sh.r0) & (idx < sh.r1)
             rows = np.repeat(np.arange(ip.size - 1, dtype=np.int64), np.diff(ip))
@@ -89,22 +142,28 @@ class ShardPlan:
             parts_idx.append((idx[keep].astype(np.int64) - sh.r0 + sh.hoff))
             if has_data:
                 parts_dat.append(dat[keep])
+        if sh.halo_prev_off >= 0:
+            parts_ptr.append(np.zeros(w, dtype=np.int64))          # halo rows are inputs only: empty matrix rows
         if sh.own_rows > 0:
-            ip, idx, dat, d1 = decomp.arrow_rows(B, w, nb, True, sh.r0, sh.r1)
+            ip, idx, dat, d1 = decomp.arrow_rows(B, w, nb, self.block_diagonal, sh.r0, sh.r1)
             dropped += d1
             idx = idx.astype(np.int64)
             if rank == 0:
                 # block-row 0 reaches every column: keep this rank's columns only (peers compute the rest)
                 rows = np.repeat(np.arange(ip.size - 1, dtype=np.int64), np.diff(ip))
-                keep = idx < sh.r1
+                local = self._local_cols(sh, idx)
+                keep = local >= 0
+                # rows of block-row 0 may only use this rank's own columns (halo columns belong to their owner's share)
+                keep &= ~((rows < w) & (idx >= sh.r1))
+                assert np.all(keep | (rows < w)), "entry outside the arrow / band pattern in an own block-row"
                 cnt = np.bincount(rows[keep], minlength=sh.own_rows)
                 parts_ptr.append(cnt)
-                parts_idx.append(idx[keep])
+                parts_idx.append(local[keep])
                 if has_data:
                     parts_dat.append(dat[keep])
             else:
-                local = np.where(idx < w, idx, idx - sh.r0 + sh.hoff)
-                assert np.all((idx < w) | ((idx >= sh.r0) & (idx < sh.r1))), "non-arrow entry in an own block-row"
+                local = self._local_cols(sh, idx)
+                assert np.all(local >= 0), "entry outside the arrow / band pattern in an own block-row"
                 parts_ptr.append(np.diff(ip))
                 parts_idx.append(local)
                 if has_data:
