@@ -94,6 +94,7 @@ class ArrowDecompositionMPI:
                              block_diagonal=blocks.block_diagonal, n_blocks=self.n_blocks)
             be = NcclBackend(self.comm, dev, blocks.width, plan) if self._exchange == "nccl" \
                 else CudaPeerBackend(self.comm, dev, blocks.width, plan=None if self._exchange == "p2p-direct" else plan)
+            be.layout_plan = plan
             self._engine = ShardedArrowEngine(plan, self._n_feature_columns, be)
         else:
             self._engine = ArrowEngine(blocks.decomposition, blocks.width, self._n_feature_columns,

@@ -325,6 +325,7 @@ class ShardedArrowEngine:
         hr = min(self.width, sh.rows_global)
         be.barrier()
         be.bcast_head((level, self.xi[level]), hr)
+        self._halo(level)
         out = self._other(level, self.xi[level])
         if self.mats[level] is not None and sh.local_rows > 0:
             be.spmm(self.mats[level], self.tiles[level][self.xi[level]], self.tiles[level][out])
@@ -358,9 +359,10 @@ class ShardedArrowEngine:
                          row_map=self.fwd[j], accumulate=False, forward=True)
             self.xi[j] = self.ci[j]                             # set_features(C_i) (:545)
             be.barrier()
-        # X_0 broadcast of every level (arrow_slim_mpi.py:273)
+        # X_0 broadcast of every level (arrow_slim_mpi.py:273) and, in the banded layout, the halo tiles
         for j in range(self.L):
             be.bcast_head((j, self.xi[j]), min(self.width, pl.levels[j].rows_global))
+            self._halo(j)
 
     def spmm(self):
         for j in range(self.L):
@@ -384,6 +386,19 @@ class ShardedArrowEngine:
             self.xi[j - 1] = self.ci[j - 1]                     # set_features(C_i) (:438)
             if j > 1:
                 be.barrier()
+
+    def _halo(self, j: int):
+        """banded layout: fetch the neighbouring blocks' feature rows that sit on other GPUs (the reference's
+        neighbour tile exchange, arrow_mpi.py:150-162)"""
+        sh = self.plan.levels[j]
+        w = self.width
+        for off, src in ((sh.halo_prev_off, sh.halo_prev_src), (sh.halo_next_off, sh.halo_next_src)):
+            if off is None or off < 0 or src is None:
+                continue
+            g, first_row = src
+            peer_sh_r0 = int(sh.bounds[g])
+            self.be.copy_rows_from_peer(dst=(j, self.xi[j]), dst_off=off, peer=g, src=(j, self.xi[j]),
+                                        src_off=self.plan.hoff_of(j, g) + first_row - peer_sh_r0, rows=w)
 
     def _spmm_one(self, j: int):
         out = self._other(j, self.xi[j])
@@ -409,12 +424,14 @@ class ShardedArrowEngine:
             self.xi[j] = self.ci[j]
             be.barrier(side=True)
         be.bcast_head((0, self.xi[0]), min(self.width, pl.levels[0].rows_global))
+        self._halo(0)
         be.limit_spmm(self.overlap_ctas)        # leave SM resources to the exchange kernels on the side lane
         self._spmm_one(0)
         be.limit_spmm(0)
         be.side_join()
         for j in range(1, self.L):
             be.bcast_head((j, self.xi[j]), min(self.width, pl.levels[j].rows_global))
+            self._halo(j)
             self._spmm_one(j)
         self.aggregate()
 
@@ -603,7 +620,7 @@ class CudaPeerBackend:
         srcs = []
         for g in range(self.world):
             own = int(src_bounds[g + 1] - src_bounds[g])
-            hoff = self._hoff(g)
+            hoff = self._hoff(g, src[0])
             srcs.append(self._view(g, src[0], src[1], hoff if own > 0 else 0, max(own, 0)))
         self.ctx.gather_rows_multi(d, srcs, [int(b) for b in src_bounds], row_map, accumulate=accumulate)
 
@@ -660,8 +677,16 @@ class CudaPeerBackend:
                 if side:
                     self.ctx.set_lane(0)
 
-    def _hoff(self, g: int) -> int:
+    def _hoff(self, g: int, level: int = 0) -> int:
+        plan = self.plan if self.plan is not None else getattr(self, "layout_plan", None)
+        if plan is not None:
+            return plan.hoff_of(level, g)
         return self.width if g > 0 else 0
+
+    def copy_rows_from_peer(self, dst, dst_off, peer, src, src_off, rows):
+        d = self._view(self.rank, dst[0], dst[1], dst_off, rows)
+        sv = self._view(peer, src[0], src[1], src_off, rows)
+        d.copy_from(sv, rows=rows)
 
     def bcast_head(self, tile, rows):
         """Every GPU > 0 copies GPU 0's head tile (peer read over NVLink)."""
@@ -705,6 +730,9 @@ class NcclBackend(CudaPeerBackend):
         # legacy default stream (handle 0), which CUDA also names cudaStreamLegacy = 0x1
         super().__init__(comm, device, width, stream=torch.cuda.current_stream().cuda_stream or 1)
         self.plan_nccl = plan
+        self.layout_plan = plan
+        if not plan.block_diagonal:
+            raise NotImplementedError("the NCCL backend covers the block-diagonal layout; use exchange='p2p' for banded")
         self._tables = {}
         self._bufs = {}
 
@@ -780,13 +808,14 @@ class ShardedArrowDecomposition:
     """Convenience wrapper used by bench.py at N > 1: plan + CUDA peer backend + the reference-like calls."""
 
     def __init__(self, comm, decomposition, width: int, k: int, device: int = 0, exchange: str = "p2p",
-                 overlap: bool = False):
+                 overlap: bool = False, block_diagonal: bool = True):
         self.comm = comm
-        plan = ShardPlan(decomposition, width, comm.Get_rank(), comm.Get_size())
+        plan = ShardPlan(decomposition, width, comm.Get_rank(), comm.Get_size(), block_diagonal=block_diagonal)
         if exchange == "p2p":
             be = CudaPeerBackend(comm, device, width, plan=plan)
         elif exchange == "p2p-direct":
             be = CudaPeerBackend(comm, device, width)
+            be.layout_plan = plan
         elif exchange == "nccl":
             be = NcclBackend(comm, device, width, plan)
         else:

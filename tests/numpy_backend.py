@@ -17,8 +17,8 @@ class _Map:
 
 
 class GlooNumpyBackend:
-    def __init__(self, comm, width):
-        self.comm, self.width = comm, width
+    def __init__(self, comm, width, plan=None):
+        self.comm, self.width, self.plan = comm, width, plan
         self.rank, self.world = comm.Get_rank(), comm.Get_size()
         self.ctx = None
         self.snap = None
@@ -80,12 +80,15 @@ class GlooNumpyBackend:
             sel = np.flatnonzero((m >= src_bounds[g]) & (m < src_bounds[g + 1]))
             if sel.size == 0:
                 continue
-            hoff = self.width if g > 0 else 0
+            hoff = self.plan.hoff_of(src[0], g) if self.plan is not None else (self.width if g > 0 else 0)
             rows = self._tile(g, src[0], src[1])[hoff + m[sel] - src_bounds[g]]
             if accumulate:
                 d[dst_off + sel] += rows
             else:
                 d[dst_off + sel] = rows
+
+    def copy_rows_from_peer(self, dst, dst_off, peer, src, src_off, rows):
+        self.tiles[dst[0]][dst[1]][dst_off:dst_off + rows] = self._tile(peer, src[0], src[1])[src_off:src_off + rows]
 
     def bcast_head(self, tile, rows):
         if self.rank > 0:

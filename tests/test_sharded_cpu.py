@@ -37,17 +37,23 @@ def _worker(rank, world, port, case, q, overlap=False):
             g = GoldenCase(case.split(":", 1)[1])
             dec, w, k = g.decomposition, g.width, g.k
             Xs = g.X
+            bd = g.block_diagonal
         else:
             w, t0, k, levels, kind, nested = {"L2": (16, 7, 8, 2, "random", True), "L3": (8, 9, 5, 3, "random", True),
-                                              "L3stale": (8, 6, 4, 3, "random", False), "small": (8, 2, 4, 2, "random", True)}[case]
-            dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind=kind, seed=77, nested=nested, hub_rows=2, hub_nnz=40)
+                                              "L3stale": (8, 6, 4, 3, "random", False), "small": (8, 2, 4, 2, "random", True),
+                                              "banded": (8, 9, 4, 2, "random", True)}[case]
+            dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind=kind, seed=77, nested=nested, hub_rows=2, hub_nnz=40,
+                                            band_nnz=3 if case == "banded" else 0, shrink=1 if case == "banded" else 2)
             rng = np.random.default_rng(5)
             n0 = t0 * w
             Xs = [synth.generate_dense_matrix(n0, k, np.float32, rng), None, synth.generate_dense_matrix(n0, k, np.float32, rng)]
-        plan = ShardPlan(dec, w, rank, world)
-        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w), overlap=overlap)
+        bd = locals().get("bd", True)
+        if case == "banded":
+            bd = False
+        plan = ShardPlan(dec, w, rank, world, block_diagonal=bd)
+        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=overlap)
         assert eng.overlap == overlap
-        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=bd)
         assert eng.total_nnz == sum(M.nnz for M in po.mats)
         sh0 = plan.levels[0]
         for it, X in enumerate(Xs):
@@ -73,7 +79,9 @@ def _worker(rank, world, port, case, q, overlap=False):
 @pytest.mark.parametrize("world,case,overlap", [(w, c, False) for w in (2, 3) for c in
                                                 ["L2", "L3", "L3stale", "small", "golden:slim_L2_random_k4",
                                                  "golden:slim_L3_nonnested_k3"]] +
-                         [(2, "L3", True), (3, "L2", True), (3, "L3stale", True)])
+                         [(2, "L3", True), (3, "L2", True), (3, "L3stale", True)] +
+                         [(2, "banded", False), (3, "banded", True), (4, "banded", False),
+                          (2, "golden:wide_L2_banded_k4", False), (3, "golden:wide_L2_banded_k4", True)])
 def test_sharded_engine_over_gloo(world, case, overlap):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
