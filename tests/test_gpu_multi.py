@@ -39,12 +39,14 @@ def _worker(rank, world, port, case, exchange, q):
         from arrow_matrix_b200.sharded import ShardedArrowDecomposition
         from oracle import oracle
         w, t0, k, levels, nested = {"L2k128": (128, 9, 128, 2, True), "L3k16": (64, 11, 16, 3, True),
-                                    "L3stale_k6": (32, 6, 6, 3, False)}[case]
-        dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600)
+                                    "L3stale_k6": (32, 6, 6, 3, False), "banded_k8": (32, 9, 8, 2, True)}[case]
+        banded = case.startswith("banded")
+        dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600,
+                                        band_nnz=4 if banded else 0, shrink=1 if banded else 2)
         arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank, exchange=exchange.split("+")[0],
-                                          overlap=exchange.endswith("+overlap"))
+                                          overlap=exchange.endswith("+overlap"), block_diagonal=not banded)
         eng = arrow.engine
-        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=not banded)
         rng = np.random.default_rng(2)
         sh0 = eng.plan.levels[0]
         for it in range(3):
@@ -73,8 +75,10 @@ def _worker(rank, world, port, case, exchange, q):
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
 @pytest.mark.parametrize("exchange", ["p2p", "p2p+overlap", "p2p-direct", "nccl"])
-@pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6"])
+@pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6", "banded_k8"])
 def test_sharded_engine_on_gpus(case, exchange):
+    if case.startswith("banded") and exchange == "nccl":
+        pytest.skip("the NCCL backend covers the block-diagonal layout only")
     import torch.multiprocessing as mp
     world = min(_n_gpus(), 4)
     ctx = mp.get_context("spawn")
