@@ -1090,13 +1090,15 @@ int launch_tiles_gv(arrow_ctx *ctx, const TileArgs &t, bool rowmap, bool acc) {
 #define LAUNCH_TL(KERNEL)                                                                             \
     do {                                                                                              \
         auto fn = KERNEL;                                                                             \
-        static bool attr_set = false;                                                                 \
-        static int occ = 0;                                                                           \
-        if (!attr_set) {                                                                              \
+        static bool attr_set[64] = {};            /* function attributes are per device */            \
+        static int occ_dev[64] = {};                                                                  \
+        const int dv = ctx->device & 63;                                                              \
+        if (!attr_set[dv]) {                                                                          \
             cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);         \
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, TILE_THREADS, SMEM) != cudaSuccess || occ < 1) occ = 1; \
-            attr_set = true;                                                                          \
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[dv], fn, TILE_THREADS, SMEM) != cudaSuccess || occ_dev[dv] < 1) occ_dev[dv] = 1; \
+            attr_set[dv] = true;                                                                      \
         }                                                                                             \
+        const int occ = occ_dev[dv];                                                                  \
         const int per_sm = (ctx->spmm_ctas_per_sm > 0) ? std::min(occ, ctx->spmm_ctas_per_sm) : occ;   \
         int grid = (int)std::min<long long>((long long)per_sm * ctx->sm_count, t.n_tiles);            \
         fn<<<grid, TILE_THREADS, SMEM, ctx->stream>>>(t);                                             \
