@@ -79,6 +79,8 @@ def _worker(rank, world, port, case, exchange, q):
 def test_sharded_engine_on_gpus(case, exchange):
     if case.startswith("banded") and exchange == "nccl":
         pytest.skip("the NCCL backend covers the block-diagonal layout only")
+    if case.startswith("banded") and os.environ.get("ARROW_TEST_BANDED_GPU") != "1":
+        pytest.skip("banded layout on N GPUs is gloo-validated only so far; set ARROW_TEST_BANDED_GPU=1 to run it on hardware")
     import torch.multiprocessing as mp
     world = min(_n_gpus(), 4)
     ctx = mp.get_context("spawn")
