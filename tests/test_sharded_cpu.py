@@ -154,3 +154,48 @@ def test_a2a_tables_simulated_exchange():
                     hi = lo + int(T[d]["recv_counts"][s])
                     pos = T[d]["unpack"][(T[d]["unpack"] >= lo) & (T[d]["unpack"] < hi)]
                     assert np.all(np.diff(pos) > 0)
+
+
+@pytest.mark.parametrize("block_diagonal", [True, False])
+def test_shard_plan_algebra_without_comm(block_diagonal):
+    """local matrices x local tiles (head tile, halos, own rows) re-assemble the level's arrow product exactly"""
+    sys.path.insert(0, ROOT)
+    from scipy import sparse
+    from arrow_matrix_b200 import synth
+    from arrow_matrix_b200.sharded import ShardPlan
+    from oracle import oracle
+    w, t0, k = 8, 9, 3
+    dec = synth.synth_decomposition(t0, w, levels=2, seed=13, hub_rows=2, hub_nnz=30,
+                                    band_nnz=0 if block_diagonal else 3, shrink=1)
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 4, 5, 9, 12):
+        plans = [ShardPlan(dec, w, r, world, block_diagonal=block_diagonal) for r in range(world)]
+        for j in range(2):
+            nb = plans[0].n_blocks[j]
+            M = oracle.arrow_mask(dec[j][0], w, nb, block_diagonal)
+            X = rng.random((nb * w, k), dtype=np.float32).astype(np.float64)
+            ref = M.astype(np.float64) @ X
+            C = np.zeros_like(ref)
+            head = np.zeros((w, k))
+            for r, pl in enumerate(plans):
+                sh = pl.levels[j]
+                Xl = np.zeros((sh.local_rows, k))
+                if r > 0:
+                    Xl[:w] = X[:w]
+                Xl[sh.hoff:sh.hoff + sh.own_rows] = X[sh.r0:sh.r1]
+                if sh.halo_prev_off >= 0:
+                    g, first = sh.halo_prev_src
+                    assert plans[g].levels[j].r0 <= first < plans[g].levels[j].r1
+                    Xl[sh.halo_prev_off:sh.halo_prev_off + w] = X[first:first + w]
+                if sh.halo_next_off >= 0:
+                    g, first = sh.halo_next_src
+                    assert plans[g].levels[j].r0 <= first < plans[g].levels[j].r1
+                    Xl[sh.halo_next_off:sh.halo_next_off + w] = X[first:first + w]
+                Ml = sparse.csr_matrix((sh.data.astype(np.float64), sh.indices, sh.indptr), shape=(sh.local_rows, sh.local_rows))
+                Cl = Ml @ Xl
+                C[sh.r0:sh.r1] = Cl[sh.hoff:sh.hoff + sh.own_rows]
+                if r > 0:
+                    head += Cl[:w]                       # partial C_0 of this rank (Reduce to rank 0)
+                assert pl.hoff_of(j, r) == sh.hoff
+            C[:w] += head
+            assert np.allclose(C, ref, rtol=1e-12, atol=1e-12), (world, j)
