@@ -162,3 +162,28 @@ def synth_decomposition(n_blocks0: int, width: int, levels: int = 2, perm_kind: 
             perm = out[-1][1][q]
         out.append((mat, perm))
     return out
+
+
+def barabasi_albert(n: int, m: int, seed: int = 503, dtype=np.float32) -> sparse.csr_matrix:
+    """Adjacency matrix of a Barabasi-Albert preferential-attachment graph (the reference's synthetic input,
+    ``igraph.Graph.Barabasi(n, m, 503)`` at ``arrow_bench.py:33``; igraph is unavailable, same model, different stream)."""
+    rng = np.random.default_rng(seed)
+    m = max(1, min(m, n - 1))
+    src, dst = [], []
+    pool = list(range(m))                       # start: m isolated vertices, each counted once
+    for v in range(m, n):
+        targets = set()
+        while len(targets) < m:
+            targets.add(pool[int(rng.integers(0, len(pool)))])
+        for t in targets:
+            src.append(v)
+            dst.append(t)
+        pool.extend(targets)
+        pool.extend([v] * m)
+    r = np.asarray(src + dst, dtype=np.int64)
+    c = np.asarray(dst + src, dtype=np.int64)
+    A = sparse.csr_matrix((np.ones(r.size, dtype=dtype), (r, c)), shape=(n, n))
+    A.sum_duplicates()
+    A.data[:] = 1
+    A.sort_indices()
+    return A
