@@ -21,7 +21,7 @@ from .arrow_dec_mpi import ArrowDecompositionMPI
 
 def bench_spmm(path: Optional[str], width: int, n_features: int, iterations: int, blocked: bool, device: str,
                p_per_side=3, ba_neighbors: int = 5, wandb_api_key: str = None, datatype=np.float32, slim=False,
-               npy_format=True, comm=None, verbose: bool = True):
+               npy_format=True, comm=None, verbose: bool = True, synthetic: str = "arrow"):
     assert width > 0
     comm = comm if comm is not None else comm_mod.world_comm()
     rank = comm.Get_rank()
@@ -30,9 +30,15 @@ def bench_spmm(path: Optional[str], width: int, n_features: int, iterations: int
         path = 'tmp/test_ba' + "_" + str(p_per_side) + "_" + str(ba_neighbors)
         if rank == 0:
             os.makedirs("tmp", exist_ok=True)
-            head = max(1, min(3, ba_neighbors // 2))
-            dec = synth.synth_decomposition(p_per_side, width, levels=2 if p_per_side > 1 else 1, seed=503,
-                                            head_nnz=head, diag_nnz=max(1, ba_neighbors * 2 - head))
+            if synthetic == "ba":
+                # the reference's route (arrow_bench.py:33-34): Barabasi-Albert graph -> arrow_decomposition(g, width, 3)
+                from .decomposition import arrow_decomposition
+                A = synth.barabasi_albert(p_per_side * width, ba_neighbors, 503)
+                dec = arrow_decomposition(A, width, 3, block_diagonal=blocked, seed=503)
+            else:
+                head = max(1, min(3, ba_neighbors // 2))
+                dec = synth.synth_decomposition(p_per_side, width, levels=2 if p_per_side > 1 else 1, seed=503,
+                                                head_nnz=head, diag_nnz=max(1, ba_neighbors * 2 - head))
             graphio.save_decomposition_new(dec, path, width, block_diagonal=blocked)
             print("DATASET GENERATED -- ", p_per_side * width, " vertices")
         comm.Barrier()
