@@ -199,3 +199,31 @@ def test_shard_plan_algebra_without_comm(block_diagonal):
                 assert pl.hoff_of(j, r) == sh.hoff
             C[:w] += head
             assert np.allclose(C, ref, rtol=1e-12, atol=1e-12), (world, j)
+
+
+def test_shard_plan_from_memory_mapped_files(tmp_path):
+    """the public multi-GPU path hands ShardPlan the memory-mapped npy triplets: same shards as from scipy matrices,
+    also without a data file (ones) and with int64 indices"""
+    sys.path.insert(0, ROOT)
+    from arrow_matrix_b200 import graphio, synth
+    from arrow_matrix_b200.sharded import ShardPlan
+    w, t0 = 8, 6
+    dec = synth.synth_decomposition(t0, w, levels=2, seed=21, hub_rows=2, hub_nnz=20)
+    base = str(tmp_path / "g")
+    graphio.save_decomposition_new(dec, base, w, True)
+    mm = graphio.load_decomposition_new(base, w, True, mem_map=True)
+    base2 = str(tmp_path / "jl")
+    graphio.save_decomposition_new(dec, base2, w, True, write_data=False, index_dtype=np.int64)
+    mm2 = graphio.load_decomposition_new(base2, w, True, mem_map=True)
+    for world in (1, 3):
+        for r in range(world):
+            a = ShardPlan(dec, w, r, world)
+            b = ShardPlan(mm, w, r, world)
+            c = ShardPlan(mm2, w, r, world)
+            for j in range(2):
+                sa, sb, sc = a.levels[j], b.levels[j], c.levels[j]
+                assert np.array_equal(sa.indptr, sb.indptr) and np.array_equal(sa.indices, sb.indices)
+                assert np.array_equal(sa.data, sb.data)
+                assert np.array_equal(sa.indptr, sc.indptr) and np.array_equal(sa.indices, sc.indices)
+                assert np.all(sc.data == 1.0) and sc.data.dtype == np.float32
+                assert np.array_equal(sa.fwd_map if sa.fwd_map is not None else [], sb.fwd_map if sb.fwd_map is not None else [])
