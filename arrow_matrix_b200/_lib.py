@@ -327,7 +327,7 @@ class _Handle:
 
     def _free(self, fn_name: str):
         if self.h >= 0 and self.ctx is not None and self.ctx._h:
-            getattr(self.ctx.lib, fn_name)(self.ctx._h, self.h)
+            self.ctx._check(getattr(self.ctx.lib, fn_name)(self.ctx._h, self.h))     # a refused free keeps the handle
         self.h = -1
 
 

@@ -67,6 +67,8 @@ struct Csr {
     int n_tiles = 0;
     int4 *tiles_big = nullptr;        // TILE_ROWS_BIG / TILE_NNZ_BIG variant for narrow feature tiles
     int n_tiles_big = 0;
+    int parent = -1;                  // handle of the block whose indptr / values / tiles this one shares (remapped copy)
+    int children = 0;                 // live remapped copies that share this block's arrays
     bool live = false;
 };
 
@@ -174,6 +176,26 @@ IdxMap *get_map(arrow_ctx *ctx, int h) {
 }
 
 inline int ceil_div_i64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// frees whatever device arrays the block owns (cudaFree waits for the device, so no launch can still read them)
+void csr_release(Csr &c) {
+    if (c.owns_indptr) cudaFree(c.indptr);
+    if (c.owns_indices) cudaFree(c.indices);
+    if (c.owns_vals) cudaFree(c.vals);
+    if (c.owns_long) {
+        cudaFree(c.long_tasks);
+        cudaFree(c.long_rows);
+        cudaFree(c.long_first);
+        cudaFree(c.tiles);
+        cudaFree(c.tiles_big);
+    }
+    c = Csr();
+}
+
+struct DevTmp {                       // scratch allocation released on every exit path
+    void *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -974,6 +996,14 @@ __global__ void k_to_i32(const SrcT *__restrict__ in, int *__restrict__ out, lon
     }
 }
 
+__global__ void k_check_cols(const int *__restrict__ idx, long long n, long long n_cols, int *bad) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = idx[i];
+        if (c < 0 || c >= n_cols) atomicExch(bad, 1);
+    }
+}
+
 __global__ void k_map_from_i64(const long long *__restrict__ in, int *__restrict__ out, long long n, long long limit) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -1204,18 +1234,7 @@ void arrow_ctx_destroy(arrow_ctx *ctx) {
             else if (d.ipc) cudaIpcCloseMemHandle(d.ipc_base);
         }
     for (auto &c : ctx->csrs)
-        if (c.live) {
-            if (c.owns_indptr) cudaFree(c.indptr);
-            if (c.owns_indices) cudaFree(c.indices);
-            if (c.owns_vals) cudaFree(c.vals);
-            if (c.owns_long) {
-                cudaFree(c.long_tasks);
-                cudaFree(c.long_rows);
-                cudaFree(c.long_first);
-                cudaFree(c.tiles);
-                cudaFree(c.tiles_big);
-            }
-        }
+        if (c.live) csr_release(c);
     for (auto &m : ctx->maps)
         if (m.live) cudaFree(m.p);
     for (auto &t : ctx->timers) {
@@ -1344,6 +1363,53 @@ static int build_long_rows(arrow_ctx *ctx, Csr &c, const std::vector<int> &h_ind
     return ARROW_OK;
 }
 
+// device side of arrow_csr_upload; on failure the caller releases whatever `c` already owns
+static int csr_fill(arrow_ctx *ctx, Csr &c, int64_t n_rows, int64_t n_cols, int64_t nnz, const std::vector<int> &h_indptr,
+                    const void *indices, int indices_bytes, const float *data) {
+    c.n_rows = n_rows;
+    c.n_cols = n_cols;
+    c.nnz = nnz;
+    c.owns_indptr = c.owns_indices = c.owns_vals = c.owns_long = true;     // every array below belongs to this block
+    CUDA_TRY(ctx, cudaMalloc(&c.indptr, ((size_t)n_rows + 1 + 8) * sizeof(int)));
+    CUDA_TRY(ctx, cudaMemsetAsync(c.indptr, 0, ((size_t)n_rows + 1 + 8) * sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(c.indptr, h_indptr.data(), ((size_t)n_rows + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t nz = (size_t)nnz + 8;                       // slack: bulk copies round up to 16 bytes
+    CUDA_TRY(ctx, cudaMalloc(&c.indices, nz * sizeof(int)));
+    CUDA_TRY(ctx, cudaMalloc(&c.vals, nz * sizeof(float)));
+    CUDA_TRY(ctx, cudaMemsetAsync(c.indices, 0, nz * sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(c.vals, 0, nz * sizeof(float), ctx->stream));
+    DevTmp wide, bad;
+    int hbad = 0;
+    if (nnz > 0) {
+        CUDA_TRY(ctx, cudaMalloc(&bad.p, sizeof(int)));
+        CUDA_TRY(ctx, cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+        if (indices_bytes == 4) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(c.indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            CUDA_TRY(ctx, cudaMalloc(&wide.p, (size_t)nnz * 8));
+            CUDA_TRY(ctx, cudaMemcpyAsync(wide.p, indices, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+            k_to_i32<long long><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const long long *)wide.p, c.indices, nnz, 0, (int *)bad.p);
+            ctx->launches++;
+        }
+        // a column outside [0, n_cols) would read outside the X tile: reject the block instead
+        k_check_cols<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c.indices, nnz, n_cols, (int *)bad.p);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        if (data) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(c.vals, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            k_fill<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c.vals, 1.0f, nnz);
+            ctx->launches++;
+        }
+    }
+    const int rc = build_long_rows(ctx, c, h_indptr);
+    if (rc != ARROW_OK) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the host staging arrays may go out of scope now
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (hbad) return fail(ctx, ARROW_ERR_RANGE, "a column index lies outside [0, %lld)", (long long)n_cols);
+    return ARROW_OK;
+}
+
 int arrow_csr_upload(arrow_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz, const void *indptr, int indptr_bytes,
                      const void *indices, int indices_bytes, const float *data, int *csr_out) {
     CHECK_CTX(ctx);
@@ -1380,50 +1446,13 @@ int arrow_csr_upload(arrow_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz
         return fail(ctx, ARROW_ERR_ARG, "indptr[n_rows]-indptr[0] = %d but nnz = %lld", h_indptr[n_rows], (long long)nnz);
 
     Csr c;
-    c.n_rows = n_rows;
-    c.n_cols = n_cols;
-    c.nnz = nnz;
-    CUDA_TRY(ctx, cudaMalloc(&c.indptr, ((size_t)n_rows + 1 + 8) * sizeof(int)));
-    CUDA_TRY(ctx, cudaMemsetAsync(c.indptr, 0, ((size_t)n_rows + 1 + 8) * sizeof(int), ctx->stream));
-    c.owns_indptr = true;
-    CUDA_TRY(ctx, cudaMemcpyAsync(c.indptr, h_indptr.data(), ((size_t)n_rows + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    const size_t nz = (size_t)nnz + 8;                       // slack: bulk copies round up to 16 bytes
-    CUDA_TRY(ctx, cudaMalloc(&c.indices, nz * sizeof(int)));
-    c.owns_indices = true;
-    CUDA_TRY(ctx, cudaMalloc(&c.vals, nz * sizeof(float)));
-    c.owns_vals = true;
-    CUDA_TRY(ctx, cudaMemsetAsync(c.indices, 0, nz * sizeof(int), ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(c.vals, 0, nz * sizeof(float), ctx->stream));
-    if (nnz > 0) {
-        if (indices_bytes == 4) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(c.indices, indices, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-        } else {
-            long long *tmp = nullptr;
-            int *bad = nullptr;
-            CUDA_TRY(ctx, cudaMalloc(&tmp, (size_t)nnz * 8));
-            CUDA_TRY(ctx, cudaMalloc(&bad, sizeof(int)));
-            CUDA_TRY(ctx, cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-            CUDA_TRY(ctx, cudaMemcpyAsync(tmp, indices, (size_t)nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
-            k_to_i32<long long><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(tmp, c.indices, nnz, 0, bad);
-            ctx->launches++;
-            int hbad = 0;
-            CUDA_TRY(ctx, cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(tmp);
-            cudaFree(bad);
-            if (hbad) return fail(ctx, ARROW_ERR_RANGE, "a column index does not fit int32");
-        }
-        if (data) {
-            CUDA_TRY(ctx, cudaMemcpyAsync(c.vals, data, (size_t)nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
-        } else {
-            k_fill<float><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c.vals, 1.0f, nnz);
-            ctx->launches++;
-        }
+    const int rc = csr_fill(ctx, c, n_rows, n_cols, nnz, h_indptr, indices, indices_bytes, data);
+    if (rc != ARROW_OK) {
+        cudaStreamSynchronize(ctx->stream);                  // nothing may still write into what is released next
+        cudaGetLastError();
+        csr_release(c);
+        return rc;
     }
-    int rc = build_long_rows(ctx, c, h_indptr);
-    if (rc != ARROW_OK) return rc;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // host staging vector goes out of scope
-    CUDA_TRY(ctx, cudaGetLastError());
     c.live = true;
     const int h = new_slot(ctx->csrs);
     ctx->csrs[h] = c;
@@ -1435,18 +1464,11 @@ int arrow_csr_free(arrow_ctx *ctx, int csr) {
     CHECK_CTX(ctx);
     Csr *c = get_csr(ctx, csr);
     if (!c) return fail(ctx, ARROW_ERR_HANDLE, "bad csr handle %d", csr);
+    if (c->children > 0)
+        return fail(ctx, ARROW_ERR_ARG, "csr %d still backs %d remapped block(s); free those first", csr, c->children);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (c->owns_indptr) cudaFree(c->indptr);
-    if (c->owns_indices) cudaFree(c->indices);
-    if (c->owns_vals) cudaFree(c->vals);
-    if (c->owns_long) {
-        cudaFree(c->long_tasks);
-        cudaFree(c->long_rows);
-        cudaFree(c->long_first);
-        cudaFree(c->tiles);
-        cudaFree(c->tiles_big);
-    }
-    *c = Csr();
+    if (Csr *parent = get_csr(ctx, c->parent)) parent->children--;
+    csr_release(*c);
     return ARROW_OK;
 }
 
@@ -1470,21 +1492,31 @@ int arrow_csr_remap_columns(arrow_ctx *ctx, int csr, int map, int64_t new_n_cols
     if (!c) return fail(ctx, ARROW_ERR_HANDLE, "bad csr handle %d", csr);
     if (!m) return fail(ctx, ARROW_ERR_HANDLE, "bad map handle %d", map);
     if (!csr_out) return fail(ctx, ARROW_ERR_ARG, "csr_out is null");
+    if (new_n_cols < 0 || new_n_cols > 2147483647LL || m->limit > new_n_cols)
+        return fail(ctx, ARROW_ERR_ARG, "map reaches column %lld but the remapped block has %lld columns", (long long)m->limit, (long long)new_n_cols);
+    if (c->parent >= 0) return fail(ctx, ARROW_ERR_ARG, "csr %d is itself a remapped copy; remap its source", csr);
     Csr d = *c;
     d.owns_indptr = d.owns_vals = d.owns_long = false;      // shared with the source block
     d.owns_indices = true;
     d.indices = nullptr;
     d.n_cols = new_n_cols;
     d.may_skip = true;
+    d.parent = csr;
+    d.children = 0;
     CUDA_TRY(ctx, cudaMalloc(&d.indices, ((size_t)c->nnz + 8) * sizeof(int)));
-    CUDA_TRY(ctx, cudaMemsetAsync(d.indices, 0, ((size_t)c->nnz + 8) * sizeof(int), ctx->stream));
-    if (c->nnz > 0) {
+    cudaError_t e = cudaMemsetAsync(d.indices, 0, ((size_t)c->nnz + 8) * sizeof(int), ctx->stream);
+    if (e == cudaSuccess && c->nnz > 0) {
         k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->indices, m->p, m->n, d.indices, c->nnz);
         ctx->launches++;
+        e = cudaGetLastError();
     }
-    CUDA_TRY(ctx, cudaGetLastError());
-    const int h = new_slot(ctx->csrs);
+    if (e != cudaSuccess) {
+        cudaFree(d.indices);
+        return fail(ctx, ARROW_ERR_CUDA, "column remap failed: %s", cudaGetErrorString(e));
+    }
+    const int h = new_slot(ctx->csrs);       // may grow the table: `c` is not used past this point
     ctx->csrs[h] = d;
+    ctx->csrs[csr].children++;
     *csr_out = h;
     return ARROW_OK;
 }
@@ -1499,16 +1531,23 @@ int arrow_map_upload(arrow_ctx *ctx, const int64_t *map, int64_t n, int64_t limi
     m.n = n;
     m.limit = limit;
     CUDA_TRY(ctx, cudaMalloc(&m.p, (size_t)std::max<int64_t>(n, 1) * sizeof(int)));
+    cudaError_t e = cudaSuccess;
     if (n > 0) {
-        long long *tmp = nullptr;
-        CUDA_TRY(ctx, cudaMalloc(&tmp, (size_t)n * 8));
-        CUDA_TRY(ctx, cudaMemcpyAsync(tmp, map, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        k_map_from_i64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(tmp, m.p, n, limit);
-        ctx->launches++;
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(tmp);
+        DevTmp wide;
+        e = cudaMalloc(&wide.p, (size_t)n * 8);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(wide.p, map, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            k_map_from_i64<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((const long long *)wide.p, m.p, n, limit);
+            ctx->launches++;
+            e = cudaStreamSynchronize(ctx->stream);
+        }
     }
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(m.p);
+        return fail(ctx, ARROW_ERR_CUDA, "map upload failed: %s", cudaGetErrorString(e));
+    }
     m.live = true;
     const int h = new_slot(ctx->maps);
     ctx->maps[h] = m;
@@ -1539,7 +1578,10 @@ int arrow_map_compose(arrow_ctx *ctx, int inner, int outer, int *map_out) {
         k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a->p, b->p, b->n, m.p, m.n);
         ctx->launches++;
     }
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+        cudaFree(m.p);
+        return fail(ctx, ARROW_ERR_CUDA, "map compose failed: %s", cudaGetErrorString(e));
+    }
     m.live = true;
     const int h = new_slot(ctx->maps);
     ctx->maps[h] = m;
@@ -1564,7 +1606,10 @@ int arrow_map_invert(arrow_ctx *ctx, int map, int64_t n_out, int *map_out) {
         k_map_invert<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a->p, a->n, m.p, n_out);
         ctx->launches++;
     }
-    CUDA_TRY(ctx, cudaGetLastError());
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {
+        cudaFree(m.p);
+        return fail(ctx, ARROW_ERR_CUDA, "map invert failed: %s", cudaGetErrorString(e));
+    }
     m.live = true;
     const int h = new_slot(ctx->maps);
     ctx->maps[h] = m;

@@ -76,17 +76,22 @@ int  arrow_set_option(arrow_ctx *ctx, int option, int value);
 /* ---- sparse blocks (replaces _sp2cp, sp2cp.py:6-16: uploaded once, resident) ----------------- */
 /* indptr has n_rows+1 entries of indptr_bytes (4 or 8) each and may start at any base value
  * (a row slice of a bigger file); indices/data point at the entry indptr[0] refers to.
- * data == NULL means all ones (missing _data.npy, graphio.py:292-298). */
+ * data == NULL means all ones (missing _data.npy, graphio.py:292-298).
+ * Rejected with ARROW_ERR_ARG / ARROW_ERR_RANGE (nothing stays allocated): a row pointer that is not a
+ * non-decreasing sequence spanning exactly nnz entries, a column index outside [0, n_cols), a block beyond the
+ * int32 device layout. */
 int  arrow_csr_upload(arrow_ctx *ctx, int64_t n_rows, int64_t n_cols, int64_t nnz,
                       const void *indptr, int indptr_bytes,
                       const void *indices, int indices_bytes,
                       const float *data, int *csr_out);
+/* Refused (ARROW_ERR_ARG) while remapped copies made by arrow_csr_remap_columns still share the block's arrays. */
 int  arrow_csr_free(arrow_ctx *ctx, int csr);
 int  arrow_csr_info(arrow_ctx *ctx, int csr, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
                     int64_t *max_row_nnz, int64_t *n_long_rows);
 /* New CSR sharing indptr/values with `csr`, columns sent through `map` (col' = map[col]; entries
  * whose image is invalid are skipped by the kernels).  This folds the forward permutation gather
- * (arrow_dec_mpi.py:526, 544) into the SpMM's X read. */
+ * (arrow_dec_mpi.py:526, 544) into the SpMM's X read.  `map`'s limit must not exceed new_n_cols; the copy must be
+ * freed before its source. */
 int  arrow_csr_remap_columns(arrow_ctx *ctx, int csr, int map, int64_t new_n_cols, int *csr_out);
 
 /* ---- row maps (to_prev / to_next slices, arrow_dec_mpi.py:737-749) ---------------------------- */

@@ -167,3 +167,24 @@ def test_stream_step_matches_blocking_calls(cuda_device, mode):
     for g, r in zip(got, ref):
         assert np.array_equal(g, r)
     eng.close()
+
+
+@pytest.mark.parametrize("n,w,k", [(1000, 64, 8), (630, 100, 16)])
+def test_decomposed_graph_through_engine(cuda_device, n, w, k):
+    """graph -> igraph-free arrow decomposition -> device engine == the reference protocol on the same levels
+    (ragged last block, non-nested permutations, best-effort last level)"""
+    from arrow_matrix_b200.decomposition import arrow_decomposition
+    A = synth.barabasi_albert(n, 4, seed=9)
+    dec = arrow_decomposition(A, w, max_number_of_levels=3, block_diagonal=True, seed=1)
+    eng = ArrowEngine(dec, w, k, device=cuda_device, mode="auto")
+    po = oracle.ReferenceProtocolOracle(dec, w, k)
+    rng = np.random.default_rng(6)
+    X = synth.generate_dense_matrix(po.rows[0], k, np.float32, rng)
+    eng.set_features(X)
+    po.set_features(X.copy())
+    for it in range(2):
+        eng.step()
+        po.step()
+        for j in range(po.L if eng.mode == "exchange" else 1):      # fused mode keeps only level 0's tile
+            assert_close(eng.result(j), po.C[j], tol=1e-5 if it == 0 else 3e-5)
+    eng.close()

@@ -218,6 +218,14 @@ def test_errors_are_reported(ctx):
         ctx.spmm(A, ctx.dense_alloc(4, 4), ctx.dense_alloc(8, 4))   # X too short
     with pytest.raises(_lib.ArrowError):
         ctx.csr_upload(2, 2, np.array([0, 2, 1]), np.array([0]), None)      # decreasing indptr
+    for dt in (np.int32, np.int64):
+        with pytest.raises(_lib.ArrowError):
+            ctx.csr_upload(2, 2, np.array([0, 1, 2]), np.array([0, 5], dtype=dt), None)   # column outside the block
+    remapped = A.remap_columns(ctx.map_upload(np.arange(8, dtype=np.int64), 8), 8)
+    with pytest.raises(_lib.ArrowError):
+        A.free()                                         # its arrays still back the remapped copy
+    remapped.free()
+    A.free()
 
 
 @pytest.mark.parametrize("k", [16, 128, 6, 256])

@@ -87,3 +87,21 @@ def test_bench_spmm_driver_and_cli(cuda_device, tmp_path, monkeypatch):
         arrow_bench.bench_spmm(None, 100, 2, 1, True, 'cpu', p_per_side=2, verbose=False)
     from arrow_matrix_b200 import cli
     cli.main(["-w", "50", "-c", "8", "-z", "2", "-r", "3", "-m", "4"])
+
+
+def test_bench_spmm_reference_route_ba_graph(cuda_device, tmp_path, monkeypatch):
+    """the reference's own synthetic route (arrow_bench.py:33-34): Barabasi-Albert graph -> arrow decomposition ->
+    files -> load -> iterate; the last level is best effort, so the check is against the reference protocol"""
+    monkeypatch.chdir(tmp_path)
+    out = arrow_bench.bench_spmm(None, 64, 8, 2, True, 'gpu', p_per_side=6, ba_neighbors=4, verbose=False, synthetic="ba")
+    assert len(out["times"]) == 2
+    arrow = out["arrow"]
+    dec = graphio.load_decomposition_new("tmp/test_ba_6_4", 64, True)
+    assert 1 <= len(dec) <= 3 and arrow.decomposition_length == len(dec)
+    po = oracle.ReferenceProtocolOracle(dec, 64, 8)
+    rng = np.random.default_rng(42)
+    for _ in range(2):                                   # the driver sets fresh features before every iteration
+        X = 2 * rng.random((po.rows[0], 8), dtype=np.float32) - 1
+        po.set_features(X.copy())
+        ref = po.step()
+    assert_close(arrow.B.result_tile(), ref, tol=2e-5)

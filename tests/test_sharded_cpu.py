@@ -38,6 +38,15 @@ def _worker(rank, world, port, case, q, overlap=False):
             dec, w, k = g.decomposition, g.width, g.k
             Xs = g.X
             bd = g.block_diagonal
+        elif case.startswith("decomposed"):
+            # a graph run through the igraph-free arrow decomposition (n is not a multiple of the width: ragged tail)
+            from arrow_matrix_b200.decomposition import arrow_decomposition
+            n, w, k = (630, 100, 8) if case == "decomposed" else (1000, 64, 4)
+            A = synth.barabasi_albert(n, 4, seed=9)
+            dec = arrow_decomposition(A, w, max_number_of_levels=3, block_diagonal=True, seed=1)
+            rows0 = oracle.number_of_blocks(dec[0][0], w) * w
+            rng = np.random.default_rng(6)
+            Xs = [synth.generate_dense_matrix(rows0, k, np.float32, rng), None]
         else:
             w, t0, k, levels, kind, nested = {"L2": (16, 7, 8, 2, "random", True), "L3": (8, 9, 5, 3, "random", True),
                                               "L3stale": (8, 6, 4, 3, "random", False), "small": (8, 2, 4, 2, "random", True),
@@ -81,7 +90,8 @@ def _worker(rank, world, port, case, q, overlap=False):
                                                  "golden:slim_L3_nonnested_k3"]] +
                          [(2, "L3", True), (3, "L2", True), (3, "L3stale", True)] +
                          [(2, "banded", False), (3, "banded", True), (4, "banded", False),
-                          (2, "golden:wide_L2_banded_k4", False), (3, "golden:wide_L2_banded_k4", True)])
+                          (2, "golden:wide_L2_banded_k4", False), (3, "golden:wide_L2_banded_k4", True),
+                          (2, "decomposed", False), (3, "decomposed-1000", True)])
 def test_sharded_engine_over_gloo(world, case, overlap):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
