@@ -101,3 +101,34 @@ def test_cli_flags_match_reference():
     with pytest.raises(SystemExit):
         cli.main(["--help"])
     assert cli.str2bool("yes") and not cli.str2bool("0")
+
+
+def test_wb_logging_writes_the_reference_artefacts(tmp_path, monkeypatch):
+    """same four files and the same content layout as the reference's file logger (wb_logging.py:81-114, 191-201)"""
+    import pickle
+    from arrow_matrix_b200 import wb_logging
+    from arrow_matrix_b200.comm import SelfComm
+    monkeypatch.chdir(tmp_path)
+    assert wb_logging.wandb_init(SelfComm(), "data/graphs/toy", 16, 3, "gpu", "Arrow_B200_v0.1_Slim", 100) is None
+    wb_logging.log({"init_time": 0.5})
+    for i in range(3):
+        wb_logging.set_iteration_data({"iteration": i})
+        wb_logging.log({"spmm_time": 0.1 * (i + 1)})
+    base = wb_logging.finish()
+    assert base.startswith("logs/Arrow_B200_v0.1_Slim.toy.")
+    with open(base + ".pickle", "rb") as f:
+        data = pickle.load(f)
+    assert data[0] == {"init_time": 0.5, "rank": 0}
+    assert data[3] == {"spmm_time": 0.1 * 3, "iteration": 2, "rank": 0}
+    assert open(base + ".txt").read() == str(data)
+    with open(base + ".config.pickle", "rb") as f:
+        cfg = pickle.load(f)
+    assert cfg == {"dataset": "toy", "width": 100, "n_features": 16, "iterations": 3, "device": "gpu", "ranks": 1,
+                   "host": "NA", "algorithm": "Arrow_B200_v0.1_Slim"}
+    assert open(base + ".config").read() == str(cfg)
+    runs = list(wb_logging.load_local_runs(tmp_path / "logs"))
+    assert len(runs) == 1 and runs[0][0] == cfg and runs[0][1] == data
+    open(base + ".logged", "w").close()                      # the reference marks uploaded runs this way
+    assert list(wb_logging.load_local_runs(tmp_path / "logs")) == []
+    wb_logging.wandb_init(SelfComm(), None, 4, 1, "gpu", "X", 10)
+    assert wb_logging.logs() == [] and wb_logging._CONFIG["dataset"] == "synthetic"
