@@ -31,6 +31,9 @@ class SelfComm:
     def allgather(self, obj: Any) -> List[Any]:
         return [obj]
 
+    def alltoall(self, objs: List[Any]) -> List[Any]:
+        return [objs[0]]
+
 
 class TorchComm:
     """World of ``torch.distributed`` ranks (one per GPU; NCCL on the box, gloo in the CPU tests)."""
@@ -67,6 +70,12 @@ class TorchComm:
         out = [None] * self.Get_size()
         self._dist.all_gather_object(out, obj, group=self._group)
         return out
+
+    def alltoall(self, objs: List[Any]) -> List[Any]:
+        """``objs[d]`` goes to rank ``d``; returns what every rank addressed to this one (set-up traffic only:
+        built on the object all-gather, so every rank sees all rows of the exchange matrix)."""
+        me = self.Get_rank()
+        return [row[me] for row in self.allgather(list(objs))]
 
 
 def init_from_env() -> None:

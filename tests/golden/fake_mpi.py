@@ -5,8 +5,8 @@ installed, and the reference needs one MPI rank per block-row.  Each "rank" is a
 collectives are built from one primitive -- a mailbox keyed by (communicator, per-communicator
 sequence number, source, destination) -- so blocking and non-blocking calls share the code and no
 thread barriers are needed.  Only the subset of the MPI API the reference's arrow path touches is
-provided (Bcast, Reduce, Alltoallv, Ialltoallv, Scatterv, Igatherv, Gather, Send/Recv, Isend/Irecv,
-Barrier, allreduce, gather, bcast, send/recv, groups and Comm.Create).
+provided (Bcast, Reduce, Alltoall, Alltoallv, Ialltoallv, Scatterv, Igatherv, Gather, Send/Recv, Isend/Irecv,
+Barrier, allreduce, allgather, reduce, gather, bcast, send/recv, groups and Comm.Create).
 """
 from __future__ import annotations
 
@@ -52,8 +52,9 @@ class _CommState:
         self.world_ranks = list(world_ranks)
 
 
-SUM, LOR = "SUM", "LOR"
+SUM, LOR, LAND = "SUM", "LOR", "LAND"
 FLOAT, DOUBLE, INT64_T = "FLOAT", "DOUBLE", "INT64_T"
+TAG_UB = 0                      # "unknown" -- the PETSc baseline's tag asserts accept 0 (spmm_petsc.py:161)
 
 
 class Group:
@@ -224,6 +225,10 @@ class Comm:
         seq, me, n = self._next(), self.Get_rank(), self.Get_size()
         sbuf, scounts, sdispls = _spec(sendspec)
         rbuf, rcounts, rdispls = _spec(recvspec)
+        if sdispls is None:             # mpi4py: counts without displacements mean "packed back to back"
+            sdispls = np.concatenate([[0], np.cumsum(np.asarray(scounts, dtype=np.int64))[:-1]])
+        if rdispls is None:
+            rdispls = np.concatenate([[0], np.cumsum(np.asarray(rcounts, dtype=np.int64))[:-1]])
         for d in range(n):
             c = int(scounts[d])
             off = int(sdispls[d])
@@ -242,6 +247,13 @@ class Comm:
 
     def Alltoallv(self, sendspec, recvspec):
         self._alltoallv_start(sendspec, recvspec)()
+
+    def Alltoall(self, sendbuf, recvbuf):
+        n = self.Get_size()
+        s, r = _flat(sendbuf), _flat(recvbuf)
+        per = s.size // n
+        ones = [per] * n
+        self._alltoallv_start([s, ones], [r, ones])()
 
     def Ialltoallv(self, sendspec, recvspec):
         return Request(self._alltoallv_start(sendspec, recvspec))
@@ -317,6 +329,29 @@ class Comm:
         vals = [_take(self._key(seq, s, me)) for s in range(n)]
         if op == LOR:
             return any(vals)
+        if op == LAND:
+            return all(vals)
+        acc = vals[0]
+        for v in vals[1:]:
+            acc = acc + v
+        return acc
+
+    def allgather(self, obj):
+        seq, me, n = self._next(), self.Get_rank(), self.Get_size()
+        for d in range(n):
+            _post(self._key(seq, me, d), obj)
+        return [_take(self._key(seq, s, me)) for s in range(n)]
+
+    def alltoall(self, objs):
+        seq, me, n = self._next(), self.Get_rank(), self.Get_size()
+        for d in range(n):
+            _post(self._key(seq, me, d), objs[d])
+        return [_take(self._key(seq, s, me)) for s in range(n)]
+
+    def reduce(self, obj, op=SUM, root=0):
+        vals = self.gather(obj, root)
+        if vals is None:
+            return None
         acc = vals[0]
         for v in vals[1:]:
             acc = acc + v
@@ -368,6 +403,7 @@ def install():
     mpi = types.ModuleType("mpi4py.MPI")
     mpi.Comm, mpi.Group, mpi.Request = Comm, Group, Request
     mpi.SUM, mpi.LOR, mpi.FLOAT, mpi.DOUBLE, mpi.INT64_T = SUM, LOR, FLOAT, DOUBLE, INT64_T
+    mpi.LAND, mpi.TAG_UB = LAND, TAG_UB
     mpi.COMM_WORLD = _WorldProxy()
     mpi.COMM_NULL = COMM_NULL
     pkg = types.ModuleType("mpi4py")

@@ -6,8 +6,9 @@ import numpy as np
 from scipy import sparse
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-               if not p.endswith("all_to_all_tables.npz"))
+# arrow-decomposition cases only: slim_* / wide_* (petsc_*.npz belong to the 1D baseline, all_to_all_tables.npz to the tables)
+CASES = sorted(os.path.basename(p)[:-4] for pattern in ("slim_*.npz", "wide_*.npz")
+               for p in glob.glob(os.path.join(GOLDEN_DIR, pattern)))
 
 
 class GoldenCase:

@@ -98,3 +98,69 @@ class GlooNumpyBackend:
         if self.rank == 0:
             for g in range(1, self.world):
                 self.tiles[tile[0]][tile[1]][:rows] += self._tile(g, tile[0], tile[1])[:rows]
+
+
+class GlooNumpyHaloFabric:
+    """Test double of ``baseline.spmm_petsc.CudaHaloFabric`` (numpy tiles, gloo peers, snapshot-at-barrier reads)."""
+
+    def __init__(self, comm):
+        self.comm = comm
+        self.rank, self.world = comm.Get_rank(), comm.Get_size()
+        self.snap = None
+        self.n_barriers = 0
+        self.side = False
+        self.log = []
+
+    def alloc(self, rows, k):
+        self.k = k
+        self.tiles = {n: np.zeros((int(r), k), np.float32) for n, r in rows.items()}
+
+    def csr_upload(self, A):
+        return sparse.csr_matrix(A, dtype=np.float32)
+
+    def map_upload(self, m, limit):
+        return _Map(m, max(int(limit), 1))
+
+    def h2d(self, name, row0, X):
+        self.tiles[name][row0:row0 + X.shape[0]] = X
+
+    def d2h(self, name, row0, rows, out=None):
+        if out is None:
+            return self.tiles[name][row0:row0 + rows].copy()
+        out[:] = self.tiles[name][row0:row0 + rows]
+        return out
+
+    def fill(self, name, v):
+        self.tiles[name][:] = v
+
+    def spmm(self, A, x_name, y_name, accumulate=False):
+        self.log.append(("spmm", self.side))
+        prod = A @ self.tiles[x_name][: A.shape[1]]
+        if accumulate:
+            self.tiles[y_name][:] += prod
+        else:
+            self.tiles[y_name][:] = prod
+
+    def side_begin(self):
+        self.side = True
+
+    def side_join(self):
+        self.side = False
+
+    def pack(self, dst_name, src_name, row_map):
+        assert self.side or self.world == 1
+        if row_map.n:
+            assert np.all(row_map.m >= 0)
+            self.tiles[dst_name][: row_map.n] = self.tiles[src_name][row_map.m]
+
+    def barrier(self):
+        self.snap = self.comm.allgather({n: t.copy() for n, t in self.tiles.items()})
+        self.n_barriers += 1
+
+    def pull(self, dst_name, dst_row0, peer, src_name, src_row0, rows):
+        assert peer != self.rank
+        if rows:
+            self.tiles[dst_name][dst_row0:dst_row0 + rows] = self.snap[peer][src_name][src_row0:src_row0 + rows]
+
+    def sync(self):
+        pass
