@@ -45,6 +45,7 @@ class CudaHaloFabric:
             raise ValueError("the device-side peer barrier supports at most 16 GPUs")
         self.ctx = _lib.Context(device, stream)
         self._side = False
+        self._ident = {}
 
     def alloc(self, rows: Dict[str, int], k: int):
         ctx = self.ctx
@@ -123,6 +124,16 @@ class CudaHaloFabric:
     def pull(self, dst_name, dst_row0, peer, src_name, src_row0, rows):
         if rows:
             self.view(self.rank, dst_name, dst_row0, rows).copy_from(self.view(peer, src_name, src_row0, rows), rows=rows)
+
+    def accumulate_from(self, dst_name, peer, src_name, rows):
+        """``dst[:rows] += (rank peer's src)[:rows]`` (peer read over NVLink, local read-modify-write)"""
+        if rows:
+            ident = self._ident.get(rows)
+            if ident is None:
+                ident = self.ctx.map_upload(np.arange(rows, dtype=np.int64), rows)
+                self._ident[rows] = ident
+            self.ctx.gather_rows(self.view(self.rank, dst_name, 0, rows), self.view(peer, src_name, 0, rows), ident,
+                                 accumulate=True)
 
     def sync(self):
         self.ctx.lane_sync(self.SIDE) if self.world > 1 else None

@@ -54,6 +54,7 @@ class _CommState:
 
 SUM, LOR, LAND = "SUM", "LOR", "LAND"
 FLOAT, DOUBLE, INT64_T = "FLOAT", "DOUBLE", "INT64_T"
+IN_PLACE = "IN_PLACE"
 TAG_UB = 0                      # "unknown" -- the PETSc baseline's tag asserts accept 0 (spmm_petsc.py:161)
 
 
@@ -177,6 +178,43 @@ class Comm:
                 st.world_ranks = list(group.world_ranks)
                 _comm_registry[key] = st
         return Comm(st)
+
+    # -- Cartesian topology (the 1.5D baseline's process grid)
+    def Create_cart(self, dims, periods=None, reorder=False):
+        c = self.Create(Group(self._st.world_ranks))
+        c._dims = tuple(int(d) for d in dims)
+        assert int(np.prod(c._dims)) == c.Get_size()
+        return c
+
+    def Get_coords(self, rank):
+        return [int(v) for v in np.unravel_index(int(rank), self._dims)]
+
+    def Get_cart_rank(self, coords):
+        return int(np.ravel_multi_index(tuple(int(v) for v in coords), self._dims))
+
+    def Get_topo(self):
+        return list(self._dims), [0] * len(self._dims), self.Get_coords(self.Get_rank())
+
+    def Sub(self, remain_dims):
+        mine = self.Get_coords(self.Get_rank())
+        members = [r for r in range(self.Get_size())
+                   if all(keep or a == b for keep, a, b in zip(remain_dims, self.Get_coords(r), mine))]
+        sub = self.Create(Group([self._st.world_ranks[r] for r in members]))
+        sub._dims = tuple(d for keep, d in zip(remain_dims, self._dims) if keep)
+        return sub
+
+    def Allreduce(self, sendbuf, recvbuf, op=SUM):
+        assert op == SUM
+        seq, me, n = self._next(), self.Get_rank(), self.Get_size()
+        r, _, _ = _spec(recvbuf)
+        s = r if isinstance(sendbuf, str) and sendbuf == IN_PLACE else _spec(sendbuf)[0]
+        for d in range(n):
+            _post(self._key(seq, me, d), s.copy())
+        parts = [_take(self._key(seq, src, me)) for src in range(n)]
+        acc = parts[0].copy()
+        for p_ in parts[1:]:
+            acc = acc + p_                 # rank order, same dtype: every member gets the same bits
+        r[:] = acc
 
     # -- collectives on buffers
     def Barrier(self):
@@ -403,7 +441,8 @@ def install():
     mpi = types.ModuleType("mpi4py.MPI")
     mpi.Comm, mpi.Group, mpi.Request = Comm, Group, Request
     mpi.SUM, mpi.LOR, mpi.FLOAT, mpi.DOUBLE, mpi.INT64_T = SUM, LOR, FLOAT, DOUBLE, INT64_T
-    mpi.LAND, mpi.TAG_UB = LAND, TAG_UB
+    mpi.LAND, mpi.TAG_UB, mpi.IN_PLACE = LAND, TAG_UB, IN_PLACE
+    mpi.Cartcomm = mpi.Intracomm = Comm
     mpi.COMM_WORLD = _WorldProxy()
     mpi.COMM_NULL = COMM_NULL
     pkg = types.ModuleType("mpi4py")

@@ -154,13 +154,20 @@ class GlooNumpyHaloFabric:
             self.tiles[dst_name][: row_map.n] = self.tiles[src_name][row_map.m]
 
     def barrier(self):
-        self.snap = self.comm.allgather({n: t.copy() for n, t in self.tiles.items()})
+        if self.world > 1:
+            self.snap = self.comm.allgather({n: t.copy() for n, t in self.tiles.items()})
         self.n_barriers += 1
 
+    def _peer_tile(self, peer, name):
+        return self.tiles[name] if peer == self.rank else self.snap[peer][name]
+
     def pull(self, dst_name, dst_row0, peer, src_name, src_row0, rows):
-        assert peer != self.rank
         if rows:
-            self.tiles[dst_name][dst_row0:dst_row0 + rows] = self.snap[peer][src_name][src_row0:src_row0 + rows]
+            self.tiles[dst_name][dst_row0:dst_row0 + rows] = self._peer_tile(peer, src_name)[src_row0:src_row0 + rows]
+
+    def accumulate_from(self, dst_name, peer, src_name, rows):
+        if rows:
+            self.tiles[dst_name][:rows] += self._peer_tile(peer, src_name)[:rows]
 
     def sync(self):
         pass
