@@ -237,3 +237,22 @@ def test_shard_plan_from_memory_mapped_files(tmp_path):
                 assert np.array_equal(sa.indptr, sc.indptr) and np.array_equal(sa.indices, sc.indices)
                 assert np.all(sc.data == 1.0) and sc.data.dtype == np.float32
                 assert np.array_equal(sa.fwd_map if sa.fwd_map is not None else [], sb.fwd_map if sb.fwd_map is not None else [])
+
+
+@pytest.mark.parametrize("block_diagonal,band", [(True, 0), (False, 3)])
+def test_shard_local_matrices_are_valid_uploads(block_diagonal, band):
+    """what every rank hands to arrow_csr_upload: a row pointer spanning exactly its entries and columns inside
+    [0, local_rows) -- the C ABI rejects anything else (also for ranks that own nothing)"""
+    sys.path.insert(0, ROOT)
+    from arrow_matrix_b200 import synth
+    from arrow_matrix_b200.sharded import ShardPlan
+    for (t0, w, levels, shrink) in ((7, 8, 2, 2), (9, 8, 3, 1), (2, 8, 2, 1), (5, 4, 3, 1)):
+        dec = synth.synth_decomposition(t0, w, levels=levels, seed=3, hub_rows=2, hub_nnz=20, band_nnz=band, shrink=shrink)
+        for world in (1, 2, 3, 8, 16):
+            for r in range(world):
+                pl = ShardPlan(dec, w, r, world, block_diagonal=block_diagonal)
+                for sh in pl.levels:
+                    assert sh.indptr.size == sh.local_rows + 1 and int(sh.indptr[-1]) == sh.indices.size == sh.nnz
+                    assert np.all(np.diff(sh.indptr) >= 0)
+                    if sh.nnz:
+                        assert sh.indices.min() >= 0 and sh.indices.max() < sh.local_rows
