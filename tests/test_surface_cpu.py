@@ -132,3 +132,20 @@ def test_wb_logging_writes_the_reference_artefacts(tmp_path, monkeypatch):
     assert list(wb_logging.load_local_runs(tmp_path / "logs")) == []
     wb_logging.wandb_init(SelfComm(), None, 4, 1, "gpu", "X", 10)
     assert wb_logging.logs() == [] and wb_logging._CONFIG["dataset"] == "synthetic"
+
+
+def test_plain_c_caller_binds_the_abi(tmp_path):
+    """include/arrow_b200.h compiles as strict C99 and a C program drives the library through dlopen; without a GPU
+    the library refuses to work instead of falling back to the CPU"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    _lib.load_library()                                            # builds the library if it is missing
+    so = os.path.join(ROOT, "arrow_matrix_b200", "libarrow_b200.so")
+    exe = str(tmp_path / "c_abi_caller")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-o", exe,
+                    os.path.join(ROOT, "tests", "c_abi_caller.c"), "-ldl"], check=True)
+    out = subprocess.run([exe, so], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == ("gpu 36.0" if _cuda() else "no-gpu")
