@@ -178,9 +178,10 @@ class ArrowDecompositionMPI:
         assert not slim or is_block_diagonal
         if np.dtype(datatype) != np.float32:
             raise ValueError("only float32 decompositions are supported (reference default, arrow_bench.py:21)")
-        if not use_npy:
-            raise NotImplementedError("only the npy triplet layout is supported (the reference's --npy true default)")
-        dec = graphio.load_decomposition_new(filename, width, block_diagonal=is_block_diagonal, mem_map=True)
+        if use_npy:
+            dec = graphio.load_decomposition_new(filename, width, block_diagonal=is_block_diagonal, mem_map=True)
+        else:                                  # SciPy .npz per level (``:641-648``): read whole, then sliced per rank
+            dec = graphio.load_decomposition(filename, width, block_diagonal=is_block_diagonal)
         if len(dec) == 0:
             print("ERROR: decomposition with name ", filename, " and width ", width, "not found", flush=True)
             return None, np.zeros(0, dtype=np.int32), None, None

@@ -104,6 +104,47 @@ def save_decomposition_new(decomposition: Sequence[Tuple[sparse.csr_matrix, np.n
         np.save(format_path(filename, width, i, block_diagonal, DecompositionFileType.permutation_npy), perm)
 
 
+def save_decomposition(decomposition: Sequence[Tuple[sparse.csr_matrix, np.ndarray]], filename: str, width: int,
+                       block_diagonal: bool = True, dtype=np.float32) -> None:
+    """The reference's other layout (``graphio.py:73-117``): level ``i`` as one SciPy ``.npz`` next to its
+    ``_permutation.npy``, plus the ``_nnzrows.npy`` convenience file (not read by the SpMM path)."""
+    d = os.path.dirname(filename)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    nonzero_rows = []
+    for i, (mat, perm) in enumerate(decomposition):
+        mat = sparse.csr_matrix(mat).astype(dtype)
+        sparse.save_npz(format_path(filename, width, i, block_diagonal, DecompositionFileType.npz), mat)
+        np.save(format_path(filename, width, i, block_diagonal, DecompositionFileType.permutation_npy), np.asarray(perm))
+        # the reference stores the number of isolated vertices under this name (decomposition.py:20)
+        nonzero_rows.append(int(np.count_nonzero(np.diff(mat.indptr) == 0)))
+    np.save(format_path(filename, width, 0, block_diagonal, DecompositionFileType.nonzero_rows_npy),
+            np.asarray(nonzero_rows, dtype=np.int64))
+
+
+def load_decomposition(filename: str, width: int = None, block_diagonal: bool = True, no_permutation: bool = False
+                       ) -> List[Tuple[sparse.csr_matrix, Optional[np.ndarray]]]:
+    """Read the ``.npz`` layout (``graphio.py:194-249``), including the reference's fallback to its OLD file naming
+    (``{base}_B_{width}_{i}_bd.npz``: the level index before the ``_bd`` marker) when the current one finds nothing."""
+    out = []
+    for i in range(decomposition_size(filename, width, block_diagonal)):
+        B = sparse.csr_matrix(sparse.load_npz(format_path(filename, width, i, block_diagonal, DecompositionFileType.npz)))
+        perm = None if no_permutation else np.load(format_path(filename, width, i, block_diagonal,
+                                                                DecompositionFileType.permutation_npy))
+        out.append((B, perm))
+    if not out:
+        i = 0
+        while True:
+            base = f"{filename}_B" + (f"_{width}" if width else "") + f"_{i}" + ("_bd" if block_diagonal else "")
+            if not os.path.exists(base + ".npz"):
+                break
+            B = sparse.csr_matrix(sparse.load_npz(base + ".npz"))
+            perm = None if no_permutation else np.load(base + "_permutation.npy")
+            out.append((B, perm))
+            i += 1
+    return out
+
+
 CsrTriplet = Tuple[np.ndarray, np.ndarray, np.ndarray]  # (data, indices, indptr) like the reference's mmap tuple
 
 

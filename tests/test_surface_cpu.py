@@ -149,3 +149,36 @@ def test_plain_c_caller_binds_the_abi(tmp_path):
     out = subprocess.run([exe, so], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert out.stdout.strip() == ("gpu 36.0" if _cuda() else "no-gpu")
+
+
+def test_npz_layout_roundtrip_and_old_naming(tmp_path):
+    """the reference's .npz level files (graphio.py:73-117, 194-249): current naming, the old naming fallback, and the
+    loader route of ``--npy false`` (arrow_dec_mpi.py:641-648)"""
+    from scipy import sparse
+    from arrow_matrix_b200.comm import SelfComm
+    dec = synth.synth_decomposition(5, 8, levels=2, seed=4)
+    base = str(tmp_path / "g")
+    graphio.save_decomposition(dec, base, 8, block_diagonal=True)
+    assert os.path.exists(base + "_B_8_0_bd.npz") and os.path.exists(base + "_B_8_0_bd_nnzrows.npy")
+    back = graphio.load_decomposition(base, 8, True)
+    assert len(back) == 2
+    for (B, p), (B2, p2) in zip(dec, back):
+        assert abs(sparse.csr_matrix(B) - B2).nnz == 0 and np.array_equal(p, p2)
+    blocks, n_blocks, to_prev, to_next = ArrowDecompositionMPI.load_decomposition_new(SelfComm(), base, 8, True, use_npy=False)
+    ref = ArrowDecompositionMPI.load_decomposition_new(SelfComm(), _npy_twin(dec, tmp_path), 8, True)
+    assert list(n_blocks) == list(ref[1])
+    assert all(np.array_equal(a, b) for a, b in zip(to_prev[1:], ref[2][1:]))
+    # old naming: {base}_B_{width}_{i}_bd.npz
+    old = str(tmp_path / "old")
+    for i, (B, p) in enumerate(dec):
+        sparse.save_npz(f"{old}_B_8_{i}_bd.npz", sparse.csr_matrix(B))
+        np.save(f"{old}_B_8_{i}_bd_permutation.npy", p)
+    back = graphio.load_decomposition(old, 8, True)
+    assert len(back) == 2 and abs(back[1][0] - sparse.csr_matrix(dec[1][0])).nnz == 0
+    assert graphio.load_decomposition(str(tmp_path / "missing"), 8, True) == []
+
+
+def _npy_twin(dec, tmp_path):
+    base = str(tmp_path / "twin")
+    graphio.save_decomposition_new(dec, base, 8, True)
+    return base
