@@ -20,6 +20,7 @@ from typing import List, Optional
 import numpy as np
 
 from . import decomp, graphio, wb_logging
+from .arrow_mpi import ArrowMPI
 from .arrow_slim_mpi import ArrowSlimMPI, _require_gpu
 from .engine import ArrowEngine
 
@@ -71,11 +72,13 @@ class ArrowDecompositionMPI:
         layout; on a GPU both layouts are the same row-partitioned kernels, so it is accepted and ignored."""
         assert not slim or block_diagonal
         assert np.sum(n_blocks) > 0
-        B = ArrowSlimMPI(comm)
+        def level_operator(owner, j):           # the reference hands out ArrowSlimMPI or ArrowMPI (``:166-197``)
+            return ArrowSlimMPI(comm, owner, j) if slim else ArrowMPI(comm, block_diagonal, owner, j)
+        B = level_operator(None, 0)
         arrow = ArrowDecompositionMPI(comm, B, 0, rows_per_rank, feature_columns, None, to_prev_permutation,
                                       to_next_permutation, device=device, slim=slim, block_diagonal=block_diagonal,
                                       n_blocks=[int(b) for b in n_blocks], mode=mode, exchange=exchange)
-        arrow.levels = [B] + [ArrowSlimMPI(comm, arrow, j) for j in range(1, len(n_blocks))]
+        arrow.levels = [B] + [level_operator(arrow, j) for j in range(1, len(n_blocks))]
         return arrow
 
     def _build_engine(self, blocks: DecompositionBlocks):

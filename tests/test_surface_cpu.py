@@ -182,3 +182,17 @@ def _npy_twin(dec, tmp_path):
     base = str(tmp_path / "twin")
     graphio.save_decomposition_new(dec, base, 8, True)
     return base
+
+
+def test_wide_operator_class_is_handed_out():
+    """initialize(slim=False) returns the reference's wide operator type (arrow_dec_mpi.py:166-197), slim=True the slim one"""
+    from arrow_matrix_b200.arrow_mpi import ArrowMPI
+    from arrow_matrix_b200.comm import SelfComm
+    wide = ArrowDecompositionMPI.initialize(SelfComm(), np.array([3, 2]), None, None, 8, 4, 'gpu', False, False)
+    assert type(wide.B) is ArrowMPI and wide.B.is_block_diagonal is False and len(wide.levels) == 2
+    assert all(type(lv) is ArrowMPI and lv._owner is wide for lv in wide.levels)
+    slim = ArrowDecompositionMPI.initialize(SelfComm(), np.array([3, 2]), None, None, 8, 4, 'gpu', True, True)
+    assert type(slim.B) is ArrowSlimMPI and slim.levels[1]._level == 1
+    assert issubclass(ArrowMPI, ArrowMatrix) and ArrowMPI(SelfComm()).is_block_diagonal is False
+    with pytest.raises(RuntimeError):
+        wide.B.spmm()                                   # blocks not loaded yet
