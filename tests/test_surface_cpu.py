@@ -196,3 +196,26 @@ def test_wide_operator_class_is_handed_out():
     assert issubclass(ArrowMPI, ArrowMatrix) and ArrowMPI(SelfComm()).is_block_diagonal is False
     with pytest.raises(RuntimeError):
         wide.B.spmm()                                   # blocks not loaded yet
+
+
+def test_utils_module_keeps_reference_helpers():
+    from scipy import sparse
+    from arrow_matrix_b200 import utils
+    assert utils.str2bool("yes") is True and utils.str2bool("0") is False and utils.time_to_ms(0.0125) == 12
+    rng = np.random.default_rng(0)
+    g = sparse.random(9, 9, density=0.3, format="csr", random_state=1, dtype=np.float64)
+    perm = rng.permutation(9)
+    out = utils.relabel_nodes(g, {int(i): int(p) for i, p in enumerate(perm)})
+    dense = np.zeros((9, 9))
+    d = g.toarray()
+    for a in range(9):
+        for b in range(9):
+            dense[perm[a], perm[b]] = d[a, b]
+    assert np.array_equal(out.toarray(), dense) and out.has_canonical_format
+    with pytest.raises(ValueError):
+        utils.relabel_nodes(g, {i: 0 for i in range(9)})
+    with pytest.raises(TypeError):
+        utils.relabel_nodes(g.tocsc(), {i: i for i in range(9)})
+    A = utils.generate_sparse_matrix(50, 70, 500, np.float32, rng)
+    X = utils.generate_dense_matrix(70, 3, np.float32, rng)
+    assert A.shape == (50, 70) and A.has_canonical_format and X.min() >= -1 and X.max() < 1
