@@ -153,3 +153,27 @@ def test_npy_layout_roundtrip(tmp_path):
     raw = graphio.load_decomposition_new(base2, 8, True, mem_map=True)
     assert raw[0][0][0] is None and raw[0][0][1].dtype == np.int64 and raw[0][0][2].dtype == np.int64
     assert back2[0][1].min() == 1
+
+
+@pytest.mark.parametrize("levels,k,threads", [(2, 16, 3), (3, 5, 8), (1, 4, 1)])
+def test_cpu_baseline_steps_like_the_protocol(levels, k, threads):
+    """the multi-threaded CPU baseline that bench.py times (cpu_baseline / --impl reference) computes what the pinned
+    protocol oracle computes for a step on fresh features -- bit for bit (same kernel, same order inside a row)"""
+    from oracle import cpu_parallel
+    from arrow_matrix_b200 import synth
+    w, t0 = 16, 9
+    dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=13, hub_rows=2, hub_nnz=60)
+    ref = cpu_parallel.CpuArrowReference(dec, w, k, n_threads=threads)
+    po = oracle.ReferenceProtocolOracle(dec, w, k)
+    rng = np.random.default_rng(3)
+    try:
+        for _ in range(2):                                   # fresh features per step, like arrow_bench.py:113-116
+            X = synth.generate_dense_matrix(t0 * w, k, np.float32, rng)
+            ref.set_features(X)
+            po.set_features(X.copy())
+            got = ref.step()
+            want = po.step()
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-6)
+        assert ref.flops_per_step() == 2.0 * sum(M.nnz for M in po.mats) * k
+    finally:
+        ref.close()
