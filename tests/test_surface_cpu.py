@@ -219,3 +219,20 @@ def test_utils_module_keeps_reference_helpers():
     A = utils.generate_sparse_matrix(50, 70, 500, np.float32, rng)
     X = utils.generate_dense_matrix(70, 3, np.float32, rng)
     assert A.shape == (50, 70) and A.has_canonical_format and X.min() >= -1 and X.max() < 1
+
+
+@pytest.mark.skipif(_cuda(), reason="checks the no-GPU behaviour of the documented stub")
+def test_integration_md_stub_binds_the_library():
+    """the reference-side ctypes stub printed in INTEGRATION.md section 2 is real code: it binds every symbol it names
+    with the documented signatures and reports the library's error text"""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = text.split("```python")[1].split("```")[0]
+    so = os.path.join(ROOT, "arrow_matrix_b200", "libarrow_b200.so")
+    _lib.load_library()
+    block = block.replace('ctypes.CDLL("libarrow_b200.so")', f'ctypes.CDLL({so!r})')
+    ns = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    assert {"B200", "_ck", "_L"} <= set(ns)
+    with pytest.raises(RuntimeError) as e:
+        ns["B200"](0)
+    assert "no CPU fallback" in str(e.value)
