@@ -220,10 +220,14 @@ class ShardPlan:
 class ShardedArrowEngine:
     """Executes a ShardPlan.  ``backend`` supplies device memory, kernels, peer access and barriers."""
 
-    def __init__(self, plan: ShardPlan, k: int, backend, overlap: bool = False):
+    def __init__(self, plan: ShardPlan, k: int, backend, overlap: bool = False, split_frac: float = 0.5):
         self.plan, self.k, self.be = plan, int(k), backend
         self.overlap = bool(overlap) and hasattr(backend, "side_begin")
         self.overlap_ctas = 3
+        # overlap=2 (two levels, staged exchange available): level 0 is multiplied in two row parts so that BOTH
+        # exchanges hide behind it -- forward behind part a, backward (staged into a buffer) behind part b
+        self.split = (self.overlap and int(overlap) == 2 and plan.L == 2 and plan.world > 1
+                      and getattr(backend, "supports_staged_exchange", False))
         self.rank, self.world, self.width, self.L = plan.rank, plan.world, plan.width, plan.L
         self.mode = "exchange-" + type(backend).__name__
         be = backend
@@ -237,8 +241,25 @@ class ShardedArrowEngine:
             self.bwd.append(be.map_upload(sh.bwd_map, next_rows) if sh.bwd_map is not None else None)
         # two ping-pong tiles per level, shared with the peers; level 0 gets a second pair for the streaming
         # iteration (upload of step i+1 / download of step i-1 overlap the compute of step i)
-        self.tiles = be.alloc_shared_tiles([max(sh.local_rows, 1) for sh in plan.levels], self.k,
-                                           tiles_per_level=[4] + [2] * (self.L - 1))
+        rows_per_level = [max(sh.local_rows, 1) for sh in plan.levels]
+        tiles_per_level = [4] + [2] * (self.L - 1)
+        if self.split:
+            # one more shared "level": the staging tile of the backward exchange into level 0
+            self._stage = (self.L, 0)
+            rows_per_level.append(max(int(plan.a2a_tables(0, False)["recv_counts"].sum()), 1))
+            tiles_per_level.append(1)
+            sh0 = plan.levels[0]
+            ip = np.asarray(sh0.indptr, dtype=np.int64)
+            cut = int(np.searchsorted(ip, ip[0] + split_frac * (ip[-1] - ip[0]), side="left"))
+            # part a holds the first `width` local rows: the head block on rank 0, the partial head tile elsewhere --
+            # they are reduced (read by / added on rank 0) before part b runs
+            self._cut = min(max(cut, min(self.width, sh0.local_rows)), sh0.local_rows)
+            self._parts = []
+            for r0, r1 in ((0, self._cut), (self._cut, sh0.local_rows)):
+                a, b = int(ip[r0]), int(ip[r1])
+                self._parts.append(be.csr_upload(r1 - r0, sh0.local_rows, ip[r0:r1 + 1] - a, sh0.indices[a:b], sh0.data[a:b])
+                                   if r1 > r0 else None)
+        self.tiles = be.alloc_shared_tiles(rows_per_level, self.k, tiles_per_level=tiles_per_level)
         self.xi = [0] * self.L
         self.ci = [0] * self.L
         self._pair = 0                      # which level-0 pair is active: tile index = 2*pair + {0,1}
@@ -406,7 +427,54 @@ class ShardedArrowEngine:
             self.be.spmm(self.mats[j], self.tiles[j][self.xi[j]], self.tiles[j][out])
         self.ci[j] = out
 
+    def _spmm_part(self, part: int, out: int):
+        """rows [0, cut) (part 0) or [cut, local_rows) (part 1) of this rank's level-0 product"""
+        A = self._parts[part]
+        if A is None:
+            return
+        r0, r1 = ((0, self._cut), (self._cut, self.plan.levels[0].local_rows))[part]
+        self.be.spmm(A, self.tiles[0][self.xi[0]], self.be.tile_view(0, out, r0, r1 - r0))
+
+    def _step_split(self):
+        """two levels: forward exchange || level-0 part a ; level 1 ; head reduce ; staged backward exchange ||
+        level-0 part b ; local add of the staged rows"""
+        be, pl = self.be, self.plan
+        sh0, sh1 = pl.levels
+        hr0, hr1 = min(self.width, sh0.rows_global), min(self.width, sh1.rows_global)
+        be.barrier()                                            # every rank's level-0 features are in place
+        be.side_begin()
+        be.pull_rows(dst=(1, self.ci[1]), dst_off=sh1.hoff, src=(0, self.xi[0]), src_bounds=sh0.bounds,
+                     row_map=self.fwd[1], accumulate=False, forward=True, side=True)
+        self.xi[1] = self.ci[1]
+        be.barrier(side=True)
+        be.bcast_head((0, self.xi[0]), hr0)
+        self._halo(0)
+        out0 = self._other(0, self.xi[0])
+        be.limit_spmm(self.overlap_ctas)
+        self._spmm_part(0, out0)
+        be.limit_spmm(0)
+        be.side_join()
+        be.bcast_head((1, self.xi[1]), hr1)
+        self._halo(1)
+        self._spmm_one(1)
+        self.ci[0] = out0
+        be.barrier()                                            # all partial head tiles are written (part a holds them)
+        be.reduce_head((0, self.ci[0]), hr0)
+        be.reduce_head((1, self.ci[1]), hr1)
+        be.barrier()
+        be.side_begin()
+        be.stage_rows(dst_level=0, src=(1, self.ci[1]), forward=False, stage=self._stage, side=True)
+        be.limit_spmm(self.overlap_ctas)
+        self._spmm_part(1, out0)
+        be.limit_spmm(0)
+        be.side_join()
+        # C_0[to_prev[r]] += C_1[r] (arrow_dec_mpi.py:437): the staged rows are local now
+        be.apply_staged(dst=(0, self.ci[0]), dst_off=sh0.hoff, dst_level=0, forward=False, stage=self._stage, accumulate=True)
+        self.xi[0] = self.ci[0]                                 # set_features(C_i) (:438)
+
     def step(self):
+        if self.split:
+            return self._step_split()
         if not self.overlap:
             self.propagate_features()
             self.spmm()
@@ -676,6 +744,51 @@ class CudaPeerBackend:
             finally:
                 if side:
                     self.ctx.set_lane(0)
+
+    @property
+    def supports_staged_exchange(self) -> bool:
+        return self.plan is not None and type(self) is CudaPeerBackend
+
+    def tile_view(self, level: int, which: int, off: int, rows: int):
+        return self._view(self.rank, level, which, off, rows)
+
+    def stage_rows(self, dst_level: int, src, forward: bool, stage, side: bool = False):
+        """First half of the packed exchange: pack -> barrier -> copy this rank's region of every peer's send tile,
+        back to back, into the local staging tile (plain sequential NVLink reads; nothing is added yet)."""
+        t = self._exchange_table(dst_level, forward)
+        src_sh = self.plan.levels[src[0]]
+        if side:
+            self.ctx.set_lane(self.SIDE)
+        try:
+            if t["n_send"] > 0:
+                self.ctx.gather_rows(self._raw_view(self.rank, self._send_off, t["n_send"]),
+                                     self._view(self.rank, src[0], src[1], src_sh.hoff, src_sh.own_rows), t["pack"])
+        finally:
+            if side:
+                self.ctx.set_lane(0)
+        self.barrier(side)                 # every peer's pack is complete
+        if t["n_recv"] > 0:
+            if side:
+                self.ctx.set_lane(self.SIDE)
+            try:
+                pos = 0
+                for g in range(self.world):
+                    c = t["recv_counts"][g]
+                    if c > 0:
+                        self._view(self.rank, stage[0], stage[1], pos, c).copy_from(
+                            self._raw_view(g, self._arena_base[g][1] + t["region"][g] * self.k, c), rows=c)
+                    pos += c
+            finally:
+                if side:
+                    self.ctx.set_lane(0)
+
+    def apply_staged(self, dst, dst_off: int, dst_level: int, forward: bool, stage, accumulate: bool):
+        """Second half: scatter / add the staged rows into place (local HBM only)."""
+        t = self._exchange_table(dst_level, forward)
+        n = self.plan.levels[dst[0]].own_rows
+        if n > 0 and t["n_recv"] > 0:
+            self.ctx.gather_rows(self._view(self.rank, dst[0], dst[1], dst_off, n),
+                                 self._view(self.rank, stage[0], stage[1], 0, t["n_recv"]), t["unpack"], accumulate=accumulate)
 
     def _hoff(self, g: int, level: int = 0) -> int:
         plan = self.plan if self.plan is not None else getattr(self, "layout_plan", None)

@@ -61,14 +61,53 @@ class GlooNumpyBackend:
         pass
 
     def barrier(self, side=False):
-        self.snap = self.comm.allgather([[t.copy() for t in pair] for pair in self.tiles])
+        send = getattr(self, "sendbuf", None)
+        got = self.comm.allgather(([[t.copy() for t in pair] for pair in self.tiles], None if send is None else send.copy()))
+        self.snap = [g[0] for g in got]
+        self.snap_send = [g[1] for g in got]
         self.n_barriers += 1
+
+    # -- staged (two-phase) packed exchange, mirroring CudaPeerBackend.stage_rows / apply_staged -----------------
+    supports_staged_exchange = True
+
+    def tile_view(self, level, which, off, rows):
+        return self.tiles[level][which][off:off + rows]
+
+    def _xtable(self, dst_level, forward):
+        key = (dst_level, forward)
+        cache = self.__dict__.setdefault("_xt", {})
+        if key not in cache:
+            raw = self.plan.a2a_tables(dst_level, forward)
+            counts = self.comm.allgather([int(c) for c in raw["send_counts"]])
+            cache[key] = dict(raw=raw, region=[sum(counts[s][:self.rank]) for s in range(self.world)])
+        return cache[key]
+
+    def stage_rows(self, dst_level, src, forward, stage, side=False):
+        t = self._xtable(dst_level, forward)
+        raw = t["raw"]
+        sh = self.plan.levels[src[0]]
+        self.sendbuf = self.tiles[src[0]][src[1]][sh.hoff + raw["pack"]].copy()          # pack (local)
+        self.barrier(side)                                                                # every peer's pack is complete
+        parts = [self.snap_send[g][t["region"][g]: t["region"][g] + int(raw["recv_counts"][g])] if g != self.rank
+                 else self.sendbuf[t["region"][g]: t["region"][g] + int(raw["recv_counts"][g])] for g in range(self.world)]
+        staged = np.concatenate(parts) if parts else np.zeros((0, self.k), np.float32)
+        self.tiles[stage[0]][stage[1]][: staged.shape[0]] = staged
+
+    def apply_staged(self, dst, dst_off, dst_level, forward, stage, accumulate):
+        unpack = self._xtable(dst_level, forward)["raw"]["unpack"]
+        sel = np.flatnonzero(unpack >= 0)
+        rows = self.tiles[stage[0]][stage[1]][unpack[sel]]
+        d = self.tiles[dst[0]][dst[1]]
+        if accumulate:
+            d[dst_off + sel] += rows
+        else:
+            d[dst_off + sel] = rows
 
     def allreduce_sum(self, v):
         return sum(self.comm.allgather(int(v)))
 
     def spmm(self, A, X, C):
-        C[:] = A @ X
+        C[:] = A @ X[: A.shape[1]]
 
     def _tile(self, g, level, which):
         return self.tiles[level][which] if g == self.rank else self.snap[g][level][which]

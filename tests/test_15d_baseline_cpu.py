@@ -39,53 +39,62 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, root_only, q):
+def _worker(rank, world, port, cases, q):
+    """one process per rank, all cases of a world size in one process group; a failing rank reports and exits"""
+    current = None
     try:
         sys.path.insert(0, ROOT)
         import torch.distributed as dist
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-        from arrow_matrix_b200.comm import world_comm
-        from arrow_matrix_b200.baseline import spmm_15d
-        from tests.numpy_backend import GlooNumpyHaloFabric
-        g, A = _load(name)
-        c, k = int(g["c"]), int(g["k"])
-        comm = world_comm()
-        src = A if (rank == 0 or not root_only) else None
-        if not root_only and rank % 2 == 1:                     # triplet input like generate_15d_decomposition_new
-            src = (A.data, A.indices, A.indptr)
-        fn = spmm_15d.generate_15d_decomposition_new if isinstance(src, tuple) else spmm_15d.generate_15d_decomposition
-        lA, X, Y, grid, _, _, lNKb = fn(src, k, np.float32, c, None, comm=comm, X_full=g["X_full"])
-        _check_rank(g, rank, lA, X, lNKb, grid)
-        fab = GlooNumpyHaloFabric(comm)
-        eng = spmm_15d.Spmm15D(grid, lA, X.shape[0], k, fabric=fab)
-        for it in range(2):                                     # state is reusable
-            eng.set_features(X)
-            eng.spmm()
-            got = eng.result()
-            assert got.shape == g[f"r{rank}_Y"].shape
-            assert np.allclose(got, g[f"r{rank}_Y"], rtol=1e-5, atol=1e-6), (name, rank)
-        assert fab.n_barriers == 2 * (3 if c > 1 else 2)
+        for name, root_only in cases:
+            current = name
+            _run_case(rank, name, root_only)
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
     except BaseException:     # noqa: BLE001
         import traceback
-        q.put((rank, "FAIL: " + traceback.format_exc()))
+        q.put((rank, f"FAIL in case {current}: " + traceback.format_exc()))
 
 
-@pytest.mark.parametrize("name,root_only", [("p2_c1", True), ("p4_c1", False), ("p4_c2", True), ("p4_c2_ragged", False),
-                                            ("p8_c2", False)])
-def test_15d_engine_over_gloo(name, root_only):
+def _run_case(rank, name, root_only):
+    from arrow_matrix_b200.comm import world_comm
+    from arrow_matrix_b200.baseline import spmm_15d
+    from tests.numpy_backend import GlooNumpyHaloFabric
+    g, A = _load(name)
+    c, k = int(g["c"]), int(g["k"])
+    comm = world_comm()
+    src = A if (rank == 0 or not root_only) else None
+    if not root_only and rank % 2 == 1:                     # triplet input like generate_15d_decomposition_new
+        src = (A.data, A.indices, A.indptr)
+    fn = spmm_15d.generate_15d_decomposition_new if isinstance(src, tuple) else spmm_15d.generate_15d_decomposition
+    lA, X, Y, grid, _, _, lNKb = fn(src, k, np.float32, c, None, comm=comm, X_full=g["X_full"])
+    _check_rank(g, rank, lA, X, lNKb, grid)
+    fab = GlooNumpyHaloFabric(comm)
+    eng = spmm_15d.Spmm15D(grid, lA, X.shape[0], k, fabric=fab)
+    for it in range(2):                                     # state is reusable
+        eng.set_features(X)
+        eng.spmm()
+        got = eng.result()
+        assert got.shape == g[f"r{rank}_Y"].shape
+        assert np.allclose(got, g[f"r{rank}_Y"], rtol=1e-5, atol=1e-6), (name, rank)
+    assert fab.n_barriers == 2 * (3 if c > 1 else 2)
+
+
+CASES = [("p2_c1", True), ("p4_c1", False), ("p4_c2", True), ("p4_c2_ragged", False), ("p8_c2", False)]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_15d_engine_over_gloo(world):
     import torch.multiprocessing as mp
-    g, _ = _load(name)
-    world = int(g["world"])
+    cases = [(n, r) for n, r in CASES if int(_load(n)[0]["world"]) == world]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, name, root_only, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=240) for _ in procs]
+    results = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(30)
     bad = [f"rank {rank}: {msg}" for rank, msg in sorted(results) if msg != "ok" and "Connection closed by peer" not in msg]

@@ -84,70 +84,81 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, overlap, q):
+def _worker(rank, world, port, cases, q):
+    """one process per rank, all cases of a world size in one process group; a failing rank reports and exits"""
+    current = None
     try:
         sys.path.insert(0, ROOT)
         import torch.distributed as dist
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-        from arrow_matrix_b200.comm import world_comm
-        from arrow_matrix_b200.matrix_slice import MatrixSlice
-        from arrow_matrix_b200.baseline.spmm_petsc import HaloSpmm
-        from tests.numpy_backend import GlooNumpyHaloFabric
-        comm = world_comm()
-        if case.startswith("golden:"):
-            g, A, X, all_n_i = _load(os.path.join(ROOT, "tests", "golden", f"petsc_{case[7:]}.npz"))
-            assert int(g["world"]) == world
-            Xs = [X]
-        else:
-            rng = np.random.default_rng(3)
-            sizes = {"unequal": [33] * (world // 2 + world % 2) + [5] * (world // 2), "zero": [40] + [0] * (world - 1),
-                     "big": [700] * world}[case]
-            all_n_i = np.array(sizes, dtype=np.int64)
-            n = int(all_n_i.sum())
-            A = sparse.random(n, n, density=0.03 if case != "big" else 0.004, format="csr", random_state=7, dtype=np.float32)
-            Xs = [np.round(5 * rng.random((n, 8))).astype(np.float32), (2 * rng.random((n, 8)) - 1).astype(np.float32)]
-            g = None
-        bounds = np.concatenate([[0], np.cumsum(all_n_i)])
-        s, e = int(bounds[rank]), int(bounds[rank + 1])
-        sl = MatrixSlice.initialize(comm, A[s:e])
-        assert MatrixSlice.check_comm_tables(comm, sl.x_index_in, sl.rank_in, sl.x_index_out, sl.rank_out)
-        if g is not None:
-            for key in TABLES:
-                assert np.array_equal(np.asarray(getattr(sl, key)), g[f"r{rank}_{key}"]), key
-        fab = GlooNumpyHaloFabric(comm)
-        eng = HaloSpmm(comm, sl, Xs[0].shape[1], fabric=fab, overlap=overlap)
-        assert eng.overlap == (overlap and world > 1)
-        for X in Xs:                                           # fresh features per product, state reused
-            eng.set_features(X[s:e])
-            eng.spmm()
-            Y = eng.result()
-            ref = (A @ X)[s:e]
-            assert Y.shape == ref.shape and np.allclose(Y, ref, rtol=1e-5, atol=1e-5), (case, rank)
-            assert np.array_equal(eng.halo(), X[sl.x_index_in] if sl.x_index_in.size else np.zeros((0, X.shape[1]), np.float32))
-            if g is not None:
-                assert np.allclose(Y, g[f"r{rank}_Y"], rtol=1e-5, atol=1e-6)
-        assert fab.n_barriers == (2 * len(Xs) if world > 1 else 0)
+        for case, overlap in cases:
+            current = (case, overlap)
+            _run_case(rank, world, case, overlap)
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
     except BaseException:     # noqa: BLE001
         import traceback
-        q.put((rank, "FAIL: " + traceback.format_exc()))
+        q.put((rank, f"FAIL in case {current}: " + traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world,case,overlap", [(2, "golden:unequal_w2", True), (3, "golden:unequal_w3", True),
-                                                (4, "golden:unequal_w4", False), (4, "golden:hubs_w4", True),
-                                                (3, "golden:eye_w3", True), (2, "golden:empty_w2", False),
-                                                (2, "unequal", False), (3, "zero", True), (3, "big", True)])
-def test_halo_engine_over_gloo(world, case, overlap):
+def _run_case(rank, world, case, overlap):
+    from arrow_matrix_b200.comm import world_comm
+    from arrow_matrix_b200.matrix_slice import MatrixSlice
+    from arrow_matrix_b200.baseline.spmm_petsc import HaloSpmm
+    from tests.numpy_backend import GlooNumpyHaloFabric
+    comm = world_comm()
+    if case.startswith("golden:"):
+        g, A, X, all_n_i = _load(os.path.join(ROOT, "tests", "golden", f"petsc_{case[7:]}.npz"))
+        assert int(g["world"]) == world
+        Xs = [X]
+    else:
+        rng = np.random.default_rng(3)
+        sizes = {"unequal": [33] * (world // 2 + world % 2) + [5] * (world // 2), "zero": [40] + [0] * (world - 1),
+                 "big": [700] * world}[case]
+        all_n_i = np.array(sizes, dtype=np.int64)
+        n = int(all_n_i.sum())
+        A = sparse.random(n, n, density=0.03 if case != "big" else 0.004, format="csr", random_state=7, dtype=np.float32)
+        Xs = [np.round(5 * rng.random((n, 8))).astype(np.float32), (2 * rng.random((n, 8)) - 1).astype(np.float32)]
+        g = None
+    bounds = np.concatenate([[0], np.cumsum(all_n_i)])
+    s, e = int(bounds[rank]), int(bounds[rank + 1])
+    sl = MatrixSlice.initialize(comm, A[s:e])
+    assert MatrixSlice.check_comm_tables(comm, sl.x_index_in, sl.rank_in, sl.x_index_out, sl.rank_out)
+    if g is not None:
+        for key in TABLES:
+            assert np.array_equal(np.asarray(getattr(sl, key)), g[f"r{rank}_{key}"]), key
+    fab = GlooNumpyHaloFabric(comm)
+    eng = HaloSpmm(comm, sl, Xs[0].shape[1], fabric=fab, overlap=overlap)
+    assert eng.overlap == (overlap and world > 1)
+    for X in Xs:                                           # fresh features per product, state reused
+        eng.set_features(X[s:e])
+        eng.spmm()
+        Y = eng.result()
+        ref = (A @ X)[s:e]
+        assert Y.shape == ref.shape and np.allclose(Y, ref, rtol=1e-5, atol=1e-5), (case, rank)
+        assert np.array_equal(eng.halo(), X[sl.x_index_in] if sl.x_index_in.size else np.zeros((0, X.shape[1]), np.float32))
+        if g is not None:
+            assert np.allclose(Y, g[f"r{rank}_Y"], rtol=1e-5, atol=1e-6)
+    assert fab.n_barriers == (2 * len(Xs) if world > 1 else 0)
+
+
+CASES = [(2, "golden:unequal_w2", True), (3, "golden:unequal_w3", True), (4, "golden:unequal_w4", False),
+         (4, "golden:hubs_w4", True), (3, "golden:eye_w3", True), (2, "golden:empty_w2", False),
+         (2, "unequal", False), (3, "zero", True), (3, "big", True)]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_halo_engine_over_gloo(world):
     import torch.multiprocessing as mp
+    cases = [(c, o) for w, c, o in CASES if w == world]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, overlap, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=180) for _ in procs]
+    results = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(30)
     bad = [f"rank {rank}: {msg}" for rank, msg in sorted(results) if msg != "ok" and "Connection closed by peer" not in msg]

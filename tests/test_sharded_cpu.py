@@ -20,87 +20,104 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, q, overlap=False):
+def _worker(rank, world, port, cases, q):
+    """one process per rank; the cases of one world size share the process group (a spawn + torch import per case
+    would dominate the suite's run time).  A failing rank reports and exits: its peers then fail fast on the closed
+    connection instead of waiting for it."""
+    current = None
     try:
         sys.path.insert(0, ROOT)
         import torch.distributed as dist
         dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-        from arrow_matrix_b200 import synth
-        from arrow_matrix_b200.comm import TorchComm, world_comm
-        from arrow_matrix_b200.sharded import ShardPlan, ShardedArrowEngine
-        from oracle import oracle
-        from tests.numpy_backend import GlooNumpyBackend
-        comm = world_comm()
-        assert isinstance(comm, TorchComm) and comm.Get_size() == world and comm.Get_rank() == rank
-        if case.startswith("golden:"):
-            from tests.golden_util import GoldenCase
-            g = GoldenCase(case.split(":", 1)[1])
-            dec, w, k = g.decomposition, g.width, g.k
-            Xs = g.X
-            bd = g.block_diagonal
-        elif case.startswith("decomposed"):
-            # a graph run through the igraph-free arrow decomposition (n is not a multiple of the width: ragged tail)
-            from arrow_matrix_b200.decomposition import arrow_decomposition
-            n, w, k = (630, 100, 8) if case == "decomposed" else (1000, 64, 4)
-            A = synth.barabasi_albert(n, 4, seed=9)
-            dec = arrow_decomposition(A, w, max_number_of_levels=3, block_diagonal=True, seed=1)
-            rows0 = oracle.number_of_blocks(dec[0][0], w) * w
-            rng = np.random.default_rng(6)
-            Xs = [synth.generate_dense_matrix(rows0, k, np.float32, rng), None]
-        else:
-            w, t0, k, levels, kind, nested = {"L2": (16, 7, 8, 2, "random", True), "L3": (8, 9, 5, 3, "random", True),
-                                              "L3stale": (8, 6, 4, 3, "random", False), "small": (8, 2, 4, 2, "random", True),
-                                              "banded": (8, 9, 4, 2, "random", True)}[case]
-            dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind=kind, seed=77, nested=nested, hub_rows=2, hub_nnz=40,
-                                            band_nnz=3 if case == "banded" else 0, shrink=1 if case == "banded" else 2)
-            rng = np.random.default_rng(5)
-            n0 = t0 * w
-            Xs = [synth.generate_dense_matrix(n0, k, np.float32, rng), None, synth.generate_dense_matrix(n0, k, np.float32, rng)]
-        bd = locals().get("bd", True)
-        if case == "banded":
-            bd = False
-        plan = ShardPlan(dec, w, rank, world, block_diagonal=bd)
-        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=overlap)
-        assert eng.overlap == overlap
-        po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=bd)
-        assert eng.total_nnz == sum(M.nnz for M in po.mats)
-        sh0 = plan.levels[0]
-        for it, X in enumerate(Xs):
-            if X is not None:
-                eng.set_features(X[sh0.r0:sh0.r1])
-                po.set_features(X.copy())
-            eng.step()
-            po.step()
-            for j in range(plan.L):
-                sh = plan.levels[j]
-                got = eng.result(j)
-                assert got.shape == (sh.own_rows, k)
-                assert np.allclose(got, po.C[j][sh.r0:sh.r1], rtol=1e-5, atol=1e-5), (case, rank, it, j)
-        assert comm.allreduce_lor(False) is False
+        for case, overlap in cases:
+            current = (case, overlap)
+            _run_case(rank, world, case, overlap)
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
-    except BaseException as e:     # noqa: BLE001
+    except BaseException:     # noqa: BLE001
         import traceback
-        q.put((rank, "FAIL: " + traceback.format_exc()))
+        q.put((rank, f"FAIL in case {current}: " + traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world,case,overlap", [(w, c, False) for w in (2, 3) for c in
-                                                ["L2", "L3", "L3stale", "small", "golden:slim_L2_random_k4",
-                                                 "golden:slim_L3_nonnested_k3"]] +
-                         [(2, "L3", True), (3, "L2", True), (3, "L3stale", True)] +
-                         [(2, "banded", False), (3, "banded", True), (4, "banded", False),
-                          (2, "golden:wide_L2_banded_k4", False), (3, "golden:wide_L2_banded_k4", True),
-                          (2, "decomposed", False), (3, "decomposed-1000", True)])
-def test_sharded_engine_over_gloo(world, case, overlap):
+def _run_case(rank, world, case, overlap):
+    from arrow_matrix_b200 import synth
+    from arrow_matrix_b200.comm import TorchComm, world_comm
+    from arrow_matrix_b200.sharded import ShardPlan, ShardedArrowEngine
+    from oracle import oracle
+    from tests.numpy_backend import GlooNumpyBackend
+    comm = world_comm()
+    assert isinstance(comm, TorchComm) and comm.Get_size() == world and comm.Get_rank() == rank
+    if case.startswith("golden:"):
+        from tests.golden_util import GoldenCase
+        g = GoldenCase(case.split(":", 1)[1])
+        dec, w, k = g.decomposition, g.width, g.k
+        Xs = g.X
+        bd = g.block_diagonal
+    elif case.startswith("decomposed"):
+        # a graph run through the igraph-free arrow decomposition (n is not a multiple of the width: ragged tail)
+        from arrow_matrix_b200.decomposition import arrow_decomposition
+        n, w, k = (630, 100, 8) if case == "decomposed" else (1000, 64, 4)
+        A = synth.barabasi_albert(n, 4, seed=9)
+        dec = arrow_decomposition(A, w, max_number_of_levels=3, block_diagonal=True, seed=1)
+        rows0 = oracle.number_of_blocks(dec[0][0], w) * w
+        rng = np.random.default_rng(6)
+        Xs = [synth.generate_dense_matrix(rows0, k, np.float32, rng), None]
+    else:
+        w, t0, k, levels, kind, nested = {"L2": (16, 7, 8, 2, "random", True), "L3": (8, 9, 5, 3, "random", True),
+                                          "L3stale": (8, 6, 4, 3, "random", False), "small": (8, 2, 4, 2, "random", True),
+                                          "banded": (8, 9, 4, 2, "random", True)}[case]
+        dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind=kind, seed=77, nested=nested, hub_rows=2, hub_nnz=40,
+                                        band_nnz=3 if case == "banded" else 0, shrink=1 if case == "banded" else 2)
+        rng = np.random.default_rng(5)
+        n0 = t0 * w
+        Xs = [synth.generate_dense_matrix(n0, k, np.float32, rng), None, synth.generate_dense_matrix(n0, k, np.float32, rng)]
+    bd = locals().get("bd", True)
+    if case == "banded":
+        bd = False
+    plan = ShardPlan(dec, w, rank, world, block_diagonal=bd)
+    eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=overlap)
+    assert eng.overlap == bool(overlap)
+    assert eng.split == (overlap == 2 and plan.L == 2 and world > 1)
+    po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=bd)
+    assert eng.total_nnz == sum(M.nnz for M in po.mats)
+    sh0 = plan.levels[0]
+    for it, X in enumerate(Xs):
+        if X is not None:
+            eng.set_features(X[sh0.r0:sh0.r1])
+            po.set_features(X.copy())
+        eng.step()
+        po.step()
+        for j in range(plan.L):
+            sh = plan.levels[j]
+            got = eng.result(j)
+            assert got.shape == (sh.own_rows, k)
+            assert np.allclose(got, po.C[j][sh.r0:sh.r1], rtol=1e-5, atol=1e-5), (case, rank, it, j)
+    assert comm.allreduce_lor(False) is False
+
+
+CASES = [(w, c, False) for w in (2, 3) for c in ["L2", "L3", "L3stale", "small", "golden:slim_L2_random_k4",
+                                                 "golden:slim_L3_nonnested_k3"]] + \
+        [(2, "L3", True), (3, "L2", True), (3, "L3stale", True)] + \
+        [(2, "banded", False), (3, "banded", True), (4, "banded", False),
+         (2, "golden:wide_L2_banded_k4", False), (3, "golden:wide_L2_banded_k4", True),
+         (2, "decomposed", False), (3, "decomposed-1000", True),
+         # overlap=2: split level-0 product, staged backward exchange (two levels; else falls back)
+         (2, "L2", 2), (3, "L2", 2), (4, "small", 2), (3, "golden:slim_L2_random_k4", 2),
+         (3, "golden:slim_L2_short_file_k4", 2), (3, "L3", 2)]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_sharded_engine_over_gloo(world):
     import torch.multiprocessing as mp
+    cases = [(c, o) for w, c, o in CASES if w == world]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q, overlap)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cases, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=180) for _ in procs]
+    results = [q.get(timeout=600) for _ in procs]
     for p in procs:
         p.join(30)
     bad = [f"rank {rank}: {msg}" for rank, msg in sorted(results) if msg != "ok" and "Connection closed by peer" not in msg]
