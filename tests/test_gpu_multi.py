@@ -44,7 +44,8 @@ def _worker(rank, world, port, case, exchange, q):
         dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600,
                                         band_nnz=4 if banded else 0, shrink=1 if banded else 2)
         arrow = ShardedArrowDecomposition(world_comm(), dec, w, k, device=rank, exchange=exchange.split("+")[0],
-                                          overlap=exchange.endswith("+overlap"), block_diagonal=not banded)
+                                          overlap=2 if exchange.endswith("+overlap2") else exchange.endswith("+overlap"),
+                                          block_diagonal=not banded)
         eng = arrow.engine
         po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=not banded)
         rng = np.random.default_rng(2)
@@ -74,9 +75,11 @@ def _worker(rank, world, port, case, exchange, q):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("exchange", ["p2p", "p2p+overlap", "p2p-direct", "nccl"])
+@pytest.mark.parametrize("exchange", ["p2p", "p2p+overlap", "p2p+overlap2", "p2p-direct", "nccl"])
 @pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6", "banded_k8"])
 def test_sharded_engine_on_gpus(case, exchange):
+    if exchange.endswith("+overlap2") and os.environ.get("ARROW_TEST_SPLIT_OVERLAP_GPU") != "1":
+        pytest.skip("the split overlap schedule is gloo-validated only so far; set ARROW_TEST_SPLIT_OVERLAP_GPU=1 to run it on hardware")
     if case.startswith("banded") and exchange == "nccl":
         pytest.skip("the NCCL backend covers the block-diagonal layout only")
     if case.startswith("banded") and os.environ.get("ARROW_TEST_BANDED_GPU") != "1":
