@@ -184,6 +184,19 @@ def main():
     save_case("slim_L2_short_file_k4", dec2, w, k, True, True, [feats(t0 * w, k)],
               note="features cover n_blocks[0]*width rows; rows beyond the file are padding")
 
+    # H: slim, FOUR levels, k not a multiple of 4, three chained iterations (new cases go last: the feature stream of
+    #    the earlier cases must not move)
+    w, t0, k = 4, 8, 6
+    dec = synth.synth_decomposition(t0, w, levels=4, perm_kind="random", seed=808)
+    save_case("slim_L4_nested_k6", dec, w, k, True, True, [feats(t0 * w, k), None, None],
+              note="four levels; iterations 1 and 2 are chained")
+
+    # I: wide layout, banded, THREE levels with non-nested permutations (stale rows + neighbour tiles together)
+    w, t0, k = 6, 5, 7
+    dec = synth.synth_decomposition(t0, w, levels=3, perm_kind="random", seed=909, nested=False, band_nnz=2, shrink=1)
+    save_case("wide_L3_banded_stale_k7", dec, w, k, False, False, [feats(t0 * w, k), feats(t0 * w, k), None],
+              note="non block-diagonal, three levels, rows behind the sentinel keep stale values")
+
 
 if __name__ == "__main__":
     main()

@@ -107,10 +107,10 @@ def test_arrow_pattern_masking(cuda_device):
 
 
 # ---- against golden vectors produced by the real reference (tests/golden/make_golden.py) ----------------
-from tests.golden_util import CASES, GoldenCase
+from tests.golden_util import GPU_CASES, GoldenCase
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", GPU_CASES)
 def test_engine_matches_real_reference_run(cuda_device, name):
     g = GoldenCase(name)
     eng = ArrowEngine(g.decomposition, g.width, g.k, block_diagonal=g.block_diagonal, device=cuda_device, mode="exchange")

@@ -102,6 +102,8 @@ CASES = [(w, c, False) for w in (2, 3) for c in ["L2", "L3", "L3stale", "small",
         [(2, "banded", False), (3, "banded", True), (4, "banded", False),
          (2, "golden:wide_L2_banded_k4", False), (3, "golden:wide_L2_banded_k4", True),
          (2, "decomposed", False), (3, "decomposed-1000", True),
+         (3, "golden:slim_L4_nested_k6", True), (2, "golden:wide_L3_banded_stale_k7", False),
+         (3, "golden:wide_L3_banded_stale_k7", True), (4, "golden:slim_L4_nested_k6", False),
          # overlap=2: split level-0 product, staged backward exchange (two levels; else falls back)
          (2, "L2", 2), (3, "L2", 2), (4, "small", 2), (3, "golden:slim_L2_random_k4", 2),
          (3, "golden:slim_L2_short_file_k4", 2), (3, "L3", 2)]
