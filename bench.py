@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--fused-style", type=str, default="gather", choices=["gather", "scatter"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full-size parity property (one step on all-ones features)")
     ap.add_argument("--cpu-sample-blocks", type=int, default=0)
     return ap.parse_args()
 
@@ -162,6 +163,66 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+
+# ----------------------------------------------------------------------------------------------------------
+# full-size parity property: one step on all-ones features
+# ----------------------------------------------------------------------------------------------------------
+def expected_ones_step(decomposition, width, block_diagonal=True):
+    """float64 column of ``C_0`` after ONE step on all-ones features (every feature column is the same): the row sums
+    of every level's arrow blocks pushed through the exchange maps.  Host arithmetic on the CSR arrays only -- a
+    size-independent checksum of the whole iteration (forward exchange, every product, backward scatter-add).
+    Returns ``(expected, state_free)``; ``state_free`` is False when some row lies behind the sentinel (its value then
+    depends on earlier iterations, arrow_dec_mpi.py:544) and the property does not apply."""
+    from scipy import sparse
+    from arrow_matrix_b200 import decomp
+    L = len(decomposition)
+    n_blocks = [decomp.number_of_blocks(B, width) for B, _ in decomposition]
+    _, to_prev, _, _ = decomp.prepare_permutations([p for _, p in decomposition], n_blocks, width)
+    rows = [int(b) * width for b in n_blocks]
+    x = [np.ones(rows[0])]
+    state_free = True
+    for j in range(1, L):
+        tp = to_prev[j][: rows[j]]
+        valid = tp < rows[j - 1]
+        state_free = state_free and bool(valid.all())
+        x.append(np.where(valid, x[j - 1][np.where(valid, tp, 0)], 0.0))
+    c = []
+    for j, (B, _) in enumerate(decomposition):
+        ip, idx, dat, _ = decomp.arrow_rows(B, width, n_blocks[j], block_diagonal, 0, rows[j])
+        vals = np.ones(idx.size) if dat is None else np.asarray(dat, dtype=np.float64)
+        c.append(sparse.csr_matrix((vals, idx, ip), shape=(rows[j], rows[j])) @ x[j])
+    for j in range(L - 1, 0, -1):
+        tp = to_prev[j][: rows[j]]
+        valid = tp < rows[j - 1]
+        c[j - 1][tp[valid]] += c[j][valid]                  # the maps are injective
+    return c[0], state_free
+
+
+def verify_ones_step(eng, decomposition, width, row0, hostX, hostC, comm, tol=1e-5):
+    """Run the property at the benchmark's own size, outside every timed region.  Never raises: a failure of the
+    check itself is reported in the JSON line instead of losing the measurement."""
+    try:
+        expected, state_free = expected_ones_step(decomposition, width)
+        if not state_free:
+            return {"property": "row sums (X = ones)", "skipped": "rows behind the sentinel make the result state dependent"}
+        hostX.array[:] = 1.0
+        eng.set_features(hostX.array)
+        eng.step()
+        got = eng.result(0, hostC.array)
+        n = got.shape[0]
+        exp = expected[row0: row0 + n]
+        scale = max(float(np.max(np.abs(expected))), 1e-30)
+        err = 0.0
+        for a0 in range(0, n, 1 << 20):                      # chunks: no 10 GB float64 temporary
+            a1 = min(n, a0 + (1 << 20))
+            err = max(err, float(np.max(np.abs(got[a0:a1].astype(np.float64) - exp[a0:a1, None])))) if a1 > a0 else err
+        errs = comm.allgather(err / scale)
+        worst = float(max(errs))
+        return {"property": "one step on all-ones features == row sums of every level pushed through the exchange maps",
+                "rows": int(expected.size), "max_rel_err": worst, "tolerance": tol, "ok": bool(worst <= tol)}
+    except Exception as e:     # noqa: BLE001
+        return {"property": "row sums (X = ones)", "error": f"{type(e).__name__}: {e}"}
+
 # ----------------------------------------------------------------------------------------------------------
 def run_b200(a):
     import torch
@@ -198,6 +259,7 @@ def run_b200(a):
         arrow.B.load_sparse_matrix_from_blocks(blocks)
         arrow.B.zero_rhs(a.width, a.k)
         eng = arrow._engine
+        dec = blocks.decomposition                 # memory-mapped level files (for the full-size property check)
     ctx = eng.ctx
     if a.l2_hints:
         hp, hf = (int(x) for x in a.l2_hints.split(","))
@@ -323,6 +385,12 @@ def run_b200(a):
                          f"({dt * 1e3:.0f} ms/step)"}
         ref.close()
 
+    # ---- full-size parity property (untimed; all ranks take part in the step) ----------------------------------
+    verified = None
+    if not a.no_verify:
+        row0 = eng.plan.levels[0].r0 if hasattr(eng, "plan") else 0
+        verified = verify_ones_step(eng, dec, a.width, row0, hostX, hostC, comm)
+
     if rank == 0:
         line = {"metric": "iterated SpMM GFLOP/s (k=%d)" % a.k, "value": flops / ms_step / 1e6, "unit": "GFLOP/s",
                 "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
@@ -330,7 +398,8 @@ def run_b200(a):
                 "config": {"workload": workload_name(a), "mode": eng.mode + ("/" + eng.fused_style if getattr(eng, "fused_style", None) and eng.mode == "fused" else ""), "overlap": (2 if getattr(eng, "split", False) else int(bool(getattr(eng, "overlap", False)))), "l2": "inputs larger than L2 (features 5.12 GB per pass at the default size); no flush",
                            "total_nnz": int(eng.total_nnz), "setup_s": round(t_setup, 1)},
                 "hbm_gbs_effective": alg_bytes / ms_step / 1e6, "algorithmic_bytes_per_step": alg_bytes,
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "verified": verified}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

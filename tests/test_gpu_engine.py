@@ -188,3 +188,21 @@ def test_decomposed_graph_through_engine(cuda_device, n, w, k):
         for j in range(po.L if eng.mode == "exchange" else 1):      # fused mode keeps only level 0's tile
             assert_close(eng.result(j), po.C[j], tol=1e-5 if it == 0 else 3e-5)
     eng.close()
+
+
+def test_ones_step_property_at_benchmark_scale(cuda_device):
+    """the size-independent parity property bench.py attaches to every run ("verified"): one step on all-ones features
+    equals the row sums of every level pushed through the exchange maps.  1M rows by default, the BASELINE.json size
+    (10M rows, width 10 000, k = 128) with ARROW_TEST_FULL_SIZE=1."""
+    import os
+    import bench
+    from arrow_matrix_b200.comm import SelfComm
+    full = os.environ.get("ARROW_TEST_FULL_SIZE") == "1"
+    blocks, w, k = (1000, 10000, 128) if full else (100, 10000, 128)
+    dec = synth.synth_decomposition(blocks, w, levels=2, perm_kind="random", seed=503)
+    eng = ArrowEngine(dec, w, k, device=cuda_device)
+    hx, hc = _lib.PinnedArray((blocks * w, k)), _lib.PinnedArray((blocks * w, k))
+    v = bench.verify_ones_step(eng, dec, w, 0, hx, hc, SelfComm())
+    eng.close()
+    assert v.get("ok") is True, v
+    assert v["rows"] == blocks * w and v["max_rel_err"] <= 1e-5

@@ -177,3 +177,55 @@ def test_cpu_baseline_steps_like_the_protocol(levels, k, threads):
         assert ref.flops_per_step() == 2.0 * sum(M.nnz for M in po.mats) * k
     finally:
         ref.close()
+
+
+@pytest.mark.parametrize("levels,nested", [(2, True), (3, True), (3, False), (1, True)])
+def test_bench_full_size_property_matches_the_protocol(levels, nested, tmp_path):
+    """bench.py checks every run at its own size with one step on all-ones features; its host-side expectation must be
+    what the pinned protocol computes from a zeroed state (also from the memory-mapped level files bench.py uses)"""
+    import bench
+    from arrow_matrix_b200 import graphio, synth
+    w, t0, k = 16, 9, 3
+    dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=29, nested=nested, hub_rows=2, hub_nnz=50)
+    po = oracle.ReferenceProtocolOracle(dec, w, k)
+    po.set_features(np.ones((po.rows[0], k), np.float32))
+    want = po.step()
+    got, state_free = bench.expected_ones_step(dec, w)
+    assert state_free == nested or levels == 1
+    if state_free:
+        assert got.shape == (po.rows[0],)
+        assert np.allclose(got[:, None], want, rtol=1e-5, atol=1e-5)
+        base = str(tmp_path / "g")
+        graphio.save_decomposition_new(dec, base, w, True)
+        mm = graphio.load_decomposition_new(base, w, True, mem_map=True)
+        got2, _ = bench.expected_ones_step(mm, w)
+        assert np.array_equal(got, got2)
+
+    class FakeEngine:                                    # drives verify_ones_step without a GPU
+        def __init__(self, scale=1.0):
+            self.scale = scale
+
+        def set_features(self, X):
+            po.set_features(X.copy())
+
+        def step(self):
+            self.out = po.step() * self.scale
+
+        def result(self, level, out):
+            out[:] = self.out
+            return out
+
+    class Host:
+        def __init__(self):
+            self.array = np.zeros((po.rows[0], k), np.float32)
+
+    from arrow_matrix_b200.comm import SelfComm
+    po = oracle.ReferenceProtocolOracle(dec, w, k)
+    v = bench.verify_ones_step(FakeEngine(), dec, w, 0, Host(), Host(), SelfComm())
+    if state_free:
+        assert v["ok"] and v["max_rel_err"] <= 1e-5 and v["rows"] == po.rows[0]
+        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        assert bench.verify_ones_step(FakeEngine(1.001), dec, w, 0, Host(), Host(), SelfComm())["ok"] is False
+    else:
+        assert "skipped" in v
+    assert "error" in bench.verify_ones_step(None, dec, w, 0, Host(), Host(), SelfComm()) or not state_free
