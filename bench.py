@@ -200,11 +200,24 @@ def expected_ones_step(decomposition, width, block_diagonal=True):
 
 def verify_ones_step(eng, decomposition, width, row0, hostX, hostC, comm, tol=1e-5):
     """Run the property at the benchmark's own size, outside every timed region.  Never raises: a failure of the
-    check itself is reported in the JSON line instead of losing the measurement."""
+    check itself is reported in the JSON line instead of losing the measurement, and every rank takes part in the same
+    collectives whatever happens locally (the step is collective at N > 1)."""
+    name = "one step on all-ones features == row sums of every level pushed through the exchange maps"
+    expected, state_free, problem = None, None, None
     try:
         expected, state_free = expected_ones_step(decomposition, width)
-        if not state_free:
-            return {"property": "row sums (X = ones)", "skipped": "rows behind the sentinel make the result state dependent"}
+    except Exception as e:     # noqa: BLE001
+        problem = f"{type(e).__name__}: {e}"
+    try:
+        state = comm.allgather((problem, state_free))
+    except Exception as e:     # noqa: BLE001
+        return {"property": name, "error": f"{type(e).__name__}: {e}"}
+    if any(p for p, _ in state):
+        return {"property": name, "error": next(p for p, _ in state if p)}
+    if not all(sf for _, sf in state):
+        return {"property": name, "skipped": "rows behind the sentinel make the result state dependent"}
+    rel = float("nan")
+    try:
         hostX.array[:] = 1.0
         eng.set_features(hostX.array)
         eng.step()
@@ -215,13 +228,19 @@ def verify_ones_step(eng, decomposition, width, row0, hostX, hostC, comm, tol=1e
         err = 0.0
         for a0 in range(0, n, 1 << 20):                      # chunks: no 10 GB float64 temporary
             a1 = min(n, a0 + (1 << 20))
-            err = max(err, float(np.max(np.abs(got[a0:a1].astype(np.float64) - exp[a0:a1, None])))) if a1 > a0 else err
-        errs = comm.allgather(err / scale)
-        worst = float(max(errs))
-        return {"property": "one step on all-ones features == row sums of every level pushed through the exchange maps",
-                "rows": int(expected.size), "max_rel_err": worst, "tolerance": tol, "ok": bool(worst <= tol)}
+            err = max(err, float(np.max(np.abs(got[a0:a1].astype(np.float64) - exp[a0:a1, None]))))
+        rel = err / scale
     except Exception as e:     # noqa: BLE001
-        return {"property": "row sums (X = ones)", "error": f"{type(e).__name__}: {e}"}
+        problem = f"{type(e).__name__}: {e}"
+    try:
+        outcome = comm.allgather((problem, rel))
+    except Exception as e:     # noqa: BLE001
+        return {"property": name, "error": f"{type(e).__name__}: {e}"}
+    if any(p for p, _ in outcome):
+        return {"property": name, "error": next(p for p, _ in outcome if p)}
+    worst = float(max(r for _, r in outcome))
+    return {"property": name, "rows": int(expected.size), "max_rel_err": worst, "tolerance": tol, "ok": bool(worst <= tol)}
+
 
 # ----------------------------------------------------------------------------------------------------------
 def run_b200(a):
