@@ -136,7 +136,8 @@ class CudaHaloFabric:
                                  accumulate=True)
 
     def sync(self):
-        self.ctx.lane_sync(self.SIDE) if self.world > 1 else None
+        if self.world > 1:
+            self.ctx.lane_sync(self.SIDE)
         self.ctx.sync()
 
     def close(self):
