@@ -18,3 +18,9 @@ done
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     scripts/compare_baselines.py --vertices 1000000 --neighbors 8 --width 10000 -k 128 --steps 10 --warmup 3 \
     2>gpurun_out/r2_compare.err | tee gpurun_out/r2_compare_n${N}.jsonl
+# 4. the k = 16 line of the 10M-row workload (BASELINE.json names k = 16 and 128)
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 \
+    bench.py --gpus $N --k 16 --steps 20 --warmup 5 --no-e2e --no-cpu 2>gpurun_out/r2_bench_n${N}_k16.err | tail -1 \
+    | tee gpurun_out/r2_bench_n${N}_k16.json | cut -c1-300
+timeout 600 python bench.py --k 16 --steps 20 --warmup 5 --no-cpu 2>gpurun_out/r2_bench_n1_k16.err | tail -1 \
+    | tee gpurun_out/r2_bench_n1_k16.json | cut -c1-300
