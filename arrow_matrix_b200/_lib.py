@@ -32,7 +32,11 @@ EXPORTS = [
     "arrow_spmm", "arrow_spmm_add", "arrow_gather_rows", "arrow_gather_rows_multi",
     "arrow_ipc_export", "arrow_ipc_import", "arrow_peer_barrier",
     "arrow_timer_start", "arrow_timer_stop", "arrow_timer_elapsed_ms", "arrow_launch_count", "arrow_l2_flush",
+    "arrow_ptrtable_upload", "arrow_ptrtable_free", "arrow_spmm_ex", "arrow_push_rows", "arrow_reduce_rows",
+    "arrow_graph_begin", "arrow_graph_end", "arrow_graph_launch", "arrow_graph_free",
+    "arrow_host_alloc_numa", "arrow_bind_thread_to_device_numa",
 ]
+ABI_VERSION = 2          # ARROW_ABI_VERSION of include/arrow_b200.h this binding was written against
 
 
 class ArrowError(RuntimeError):
@@ -45,16 +49,23 @@ _lib = None
 
 
 def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
-    """dlopen the in-tree library (building it with nvcc first if it is absent)."""
+    """dlopen the in-tree library.  A missing or stale library (older than its sources) is rebuilt first when nvcc
+    is available -- under a file lock and through a temporary file, so that the ranks of one ``torchrun`` never
+    dlopen a half-written file (``build.build``).  A library whose ABI version differs from this binding is refused."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise FileNotFoundError(f"{LIB_PATH} not built; run `python -m arrow_matrix_b200.build`")
-        from . import build as _build
+    from . import build as _build
+    if build_if_missing and _build.needs_build() and _build.can_build():
         _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built; run `python -m arrow_matrix_b200.build` (needs nvcc)")
     lib = ctypes.CDLL(LIB_PATH)
+    lib.arrow_b200_abi_version.restype = c_int
+    found = lib.arrow_b200_abi_version()
+    if found != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} exports ABI version {found}, this binding needs {ABI_VERSION}: rebuild it "
+                          f"(`python -m arrow_matrix_b200.build --force`)")
     P = c_void_p
     I, I64 = c_int, c_int64
     pI, pI64 = POINTER(c_int), POINTER(c_int64)
@@ -105,6 +116,17 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         "arrow_timer_elapsed_ms": (c_int, [P, I, POINTER(c_float)]),
         "arrow_launch_count": (c_int, [P, pI64]),
         "arrow_l2_flush": (c_int, [P]),
+        "arrow_ptrtable_upload": (c_int, [P, pI, I, P, P, I64, pI]),
+        "arrow_ptrtable_free": (c_int, [P, I]),
+        "arrow_spmm_ex": (c_int, [P, I, I, I, I64, I, I, I, I, I]),
+        "arrow_push_rows": (c_int, [P, pI, pI64, I, I, I]),
+        "arrow_reduce_rows": (c_int, [P, I, I, pI, I, I64]),
+        "arrow_graph_begin": (c_int, [P]),
+        "arrow_graph_end": (c_int, [P, pI]),
+        "arrow_graph_launch": (c_int, [P, I]),
+        "arrow_graph_free": (c_int, [P, I]),
+        "arrow_host_alloc_numa": (c_int, [c_size_t, I, POINTER(P)]),
+        "arrow_bind_thread_to_device_numa": (c_int, [I, pI, pI]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = the .so does not export a declared symbol
@@ -121,13 +143,17 @@ def _ptr(a: Optional[np.ndarray]) -> c_void_p:
 class PinnedArray:
     """Page-locked host staging buffer exposed as a numpy array (freed on `close()`/GC)."""
 
-    def __init__(self, shape, dtype=np.float32):
+    def __init__(self, shape, dtype=np.float32, numa_device: Optional[int] = None):
+        """``numa_device`` given: the buffer is placed on the NUMA node that GPU hangs off (arrow_host_alloc_numa)."""
         lib = load_library()
         self.shape = tuple(int(s) for s in np.atleast_1d(shape))
         self.dtype = np.dtype(dtype)
         nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         p = c_void_p()
-        rc = lib.arrow_host_alloc(c_size_t(max(nbytes, 16)), byref(p))
+        if numa_device is None:
+            rc = lib.arrow_host_alloc(c_size_t(max(nbytes, 16)), byref(p))
+        else:
+            rc = lib.arrow_host_alloc_numa(c_size_t(max(nbytes, 16)), int(numa_device), byref(p))
         if rc != 0:
             raise ArrowError(rc, (lib.arrow_last_error(None) or b"").decode())
         self._p = p
@@ -145,6 +171,15 @@ class PinnedArray:
             self.close()
         except Exception:
             pass
+
+
+def bind_thread_to_device_numa(device: int):
+    """Pin the calling thread to the CPUs of the NUMA node ``device`` hangs off; returns ``(node, n_cpus)``
+    (``(-1, 0)`` when the topology is unknown and nothing was changed)."""
+    lib = load_library()
+    node, n = c_int(-1), c_int(0)
+    lib.arrow_bind_thread_to_device_numa(int(device), byref(node), byref(n))
+    return node.value, n.value
 
 
 class Context:
@@ -186,6 +221,7 @@ class Context:
         self._check(self.lib.arrow_set_tuning(self._h, int(long_row_threshold), int(long_row_segment)))
 
     OPT_L2_HINTS_PLAIN, OPT_L2_HINTS_FUSED, OPT_BIG_TILES, OPT_SPMM_CTAS_PER_SM, OPT_PREFETCH = 1, 2, 3, 4, 5
+    OPT_ROWS_PER_GROUP, OPT_SPMM_SM_LIMIT, OPT_PUSH_CTAS, OPT_BARRIER_TIMEOUT_MS = 6, 7, 8, 9
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.arrow_set_option(self._h, int(option), int(value)))
@@ -258,6 +294,53 @@ class Context:
     def spmm_add(self, A: "Csr", X: "Dense", C: "Dense", add: "Dense", add_map: "RowMap", variant: int = VARIANT_AUTO):
         """C[r] = (A X)[r] + add[add_map[r]] (where add_map[r] >= 0)"""
         self._check(self.lib.arrow_spmm_add(self._h, A.h, X.h, C.h, add.h, add_map.h, int(variant)))
+
+    def spmm_ex(self, A: "Csr", X: "Dense", C: Optional["Dense"] = None, X2: Optional["Dense"] = None, x_split: int = 0,
+                out_table: Optional["PtrTable"] = None, add: Optional["Dense"] = None, add_map: Optional["RowMap"] = None,
+                variant: int = VARIANT_AUTO):
+        """Generalised product (``arrow_spmm_ex``): two-part X operand, row-pointer epilogue, gather-add."""
+        self._check(self.lib.arrow_spmm_ex(self._h, A.h, X.h, X2.h if X2 is not None else -1, int(x_split),
+                                           C.h if C is not None else -1, out_table.h if out_table is not None else -1,
+                                           add.h if add is not None else -1, add_map.h if add_map is not None else -1,
+                                           int(variant)))
+
+    def ptrtable_upload(self, tiles: Sequence["Dense"], which: np.ndarray, row: np.ndarray) -> "PtrTable":
+        which = np.ascontiguousarray(which, dtype=np.int32)
+        row = np.ascontiguousarray(row, dtype=np.int64)
+        assert which.shape == row.shape and which.ndim == 1
+        n = len(tiles)
+        hs = (c_int * n)(*[t.h for t in tiles])
+        h = c_int()
+        self._check(self.lib.arrow_ptrtable_upload(self._h, hs, n, _ptr(which), _ptr(row), which.size, byref(h)))
+        return PtrTable(self, h.value, which.size)
+
+    def push_rows(self, dsts: Sequence[Optional["Dense"]], item_bounds: Sequence[int], src: "Dense", m: "RowMap"):
+        n = len(dsts)
+        hs = (c_int * n)(*[(d.h if d is not None else -1) for d in dsts])
+        bd = (c_int64 * (n + 1))(*[int(b) for b in item_bounds])
+        self._check(self.lib.arrow_push_rows(self._h, hs, bd, n, src.h, m.h))
+
+    def reduce_rows(self, srcs: Sequence["Dense"], rows: int, dst: Optional["Dense"] = None,
+                    out_table: Optional["PtrTable"] = None):
+        n = len(srcs)
+        hs = (c_int * n)(*[s.h for s in srcs])
+        self._check(self.lib.arrow_reduce_rows(self._h, dst.h if dst is not None else -1,
+                                               out_table.h if out_table is not None else -1, hs, n, int(rows)))
+
+    # -- graphs -----------------------------------------------------------------------------
+    def graph_begin(self):
+        self._check(self.lib.arrow_graph_begin(self._h))
+
+    def graph_end(self) -> int:
+        h = c_int()
+        self._check(self.lib.arrow_graph_end(self._h, byref(h)))
+        return h.value
+
+    def graph_launch(self, g: int):
+        self._check(self.lib.arrow_graph_launch(self._h, int(g)))
+
+    def graph_free(self, g: int):
+        self._check(self.lib.arrow_graph_free(self._h, int(g)))
 
     def gather_rows(self, dst: "Dense", src: "Dense", m: "RowMap", accumulate: bool = False):
         self._check(self.lib.arrow_gather_rows(self._h, dst.h, src.h, m.h, ACCUMULATE if accumulate else 0))
@@ -374,6 +457,15 @@ class RowMap(_Handle):
 
     def free(self):
         self._free("arrow_map_free")
+
+
+class PtrTable(_Handle):
+    def __init__(self, ctx, h, n):
+        super().__init__(ctx, h)
+        self.n = n
+
+    def free(self):
+        self._free("arrow_ptrtable_free")
 
 
 class Dense(_Handle):

@@ -28,7 +28,7 @@ extern "C" {
 
 typedef struct arrow_ctx arrow_ctx;
 
-#define ARROW_ABI_VERSION 1
+#define ARROW_ABI_VERSION 2
 
 /* error codes */
 #define ARROW_OK              0
@@ -49,8 +49,9 @@ typedef struct arrow_ctx arrow_ctx;
 #define ARROW_VARIANT_SHFL     1  /* sub-warp per row, coalesced index/value chunk + shuffle broadcast  */
 #define ARROW_VARIANT_TMA      2  /* X rows staged into shared memory with cp.async.bulk + mbarrier     */
 #define ARROW_VARIANT_TILES    3  /* default: CSR row tiles streamed by cp.async.bulk (TMA) + mbarrier,
-                                     two stages; warps only issue X gathers.  Bits 4..7 of `variant`
-                                     optionally force the float4-per-lane count (1, 2 or 4).           */
+                                     three stages; warps only issue X gathers.  Bits 4..7 of `variant`
+                                     optionally force the float4-per-lane count (1, 2 or 4), bits 8..9 the
+                                     rows a lane group works on at once (1 or 2; 2 needs k <= 32).     */
 
 int  arrow_b200_abi_version(void);
 
@@ -68,9 +69,16 @@ int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segme
 #define ARROW_OPT_L2_HINTS_PLAIN 1
 #define ARROW_OPT_L2_HINTS_FUSED 2
 #define ARROW_OPT_BIG_TILES      3   /* 1 (default): 128-row / 2048-entry CSR tiles when k <= 32 */
-#define ARROW_OPT_PREFETCH        5   /* software L2 prefetch of the next row's X lines: bit 0 = plain launches, bit 1 = fused */
+#define ARROW_OPT_PREFETCH        5   /* bulk L2 prefetch (cp.async.bulk.prefetch.L2, one request per X row) issued per CSR tile:
+                                        low nibble = plain launches, high nibble = fused launches (row map / accumulate /
+                                        gather-add / dual X / row pointers); 0 none, 1 = the current tile's rows, 2 = the next
+                                        tile's rows (look-ahead) */
 #define ARROW_OPT_SPMM_CTAS_PER_SM 4 /* cap on resident SpMM CTAs per SM (0 = no cap): leaves SM resources to exchange
                                         kernels running on the side lane */
+#define ARROW_OPT_ROWS_PER_GROUP  6   /* 2 (default): a lane group gathers for two rows at once when k <= 32; 1: one row */
+#define ARROW_OPT_SPMM_SM_LIMIT   7   /* cap on the SMs a SpMM grid covers (0 = all): concurrent launches on two lanes share the GPU */
+#define ARROW_OPT_PUSH_CTAS       8   /* grid of arrow_push_rows (0 = 2 per SM) */
+#define ARROW_OPT_BARRIER_TIMEOUT_MS 9 /* arrow_peer_barrier gives up after this long (default 30000) and poisons the context */
 int  arrow_set_option(arrow_ctx *ctx, int option, int value);
 
 /* ---- sparse blocks (replaces _sp2cp, sp2cp.py:6-16: uploaded once, resident) ----------------- */
@@ -128,9 +136,10 @@ int  arrow_dense_h2d_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64
 int  arrow_dense_d2h_lane(arrow_ctx *ctx, int lane, int buf, int64_t row0, int64_t rows, float *host);
 int  arrow_lane_wait(arrow_ctx *ctx, int waiting_lane, int signalling_lane);
 int  arrow_lane_sync(arrow_ctx *ctx, int lane);
-/* Select the lane on which the following arrow_gather_rows[_multi] / arrow_peer_barrier / arrow_dense_copy calls
- * are launched (arrow_spmm always runs on the main lane).  Used to overlap the NVLink exchange of one level with
- * the SpMM of another; a barrier issued on lane L must use flag tiles reserved for lane L. */
+/* Select the lane on which the following arrow_spmm* / arrow_gather_rows[_multi] / arrow_push_rows / arrow_reduce_rows /
+ * arrow_peer_barrier / arrow_dense_copy calls are launched (every lane has its own tile scheduler state).  Used to run
+ * the exchange chain of the deeper levels beside the level-0 SpMM; a barrier issued on lane L must use flag tiles
+ * reserved for lane L. */
 int  arrow_set_lane(arrow_ctx *ctx, int lane);
 /* Named events for finer ordering between lanes (waiting on a never-recorded event is a no-op). */
 #define ARROW_MAX_EVENTS 16
@@ -139,6 +148,11 @@ int  arrow_event_wait(arrow_ctx *ctx, int event, int lane);
 /* pinned host staging */
 int  arrow_host_alloc(size_t bytes, void **ptr);
 int  arrow_host_free(void *ptr);
+/* Pinned staging memory placed on the NUMA node of `device` (mmap + mbind + first touch + cudaHostRegister); freed with
+ * arrow_host_free.  arrow_bind_thread_to_device_numa pins the calling thread to that node's CPUs (node_out = -1 when
+ * the topology is unknown: nothing is changed). */
+int  arrow_host_alloc_numa(size_t bytes, int device, void **ptr);
+int  arrow_bind_thread_to_device_numa(int device, int *node_out, int *n_cpus_out);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* C[out(r), :] (+)= sum_p A[r, col_p] * X[col_p, :]   for every row r of `csr`
@@ -162,13 +176,45 @@ int  arrow_gather_rows(arrow_ctx *ctx, int dst_buf, int src_buf, int map, int fl
 int  arrow_gather_rows_multi(arrow_ctx *ctx, int dst_buf, const int *src_bufs,
                              const int64_t *row_bounds, int n_src, int map, int flags);
 
+/* ---- the fused multi-GPU step ------------------------------------------------------------------- */
+/* A pointer table holds one destination per row: tile bufs[which[i]], row row[i] (which[i] < 0: the row is dropped).
+ * The tiles may be peer GPUs' memory (arrow_ipc_import): a SpMM with a pointer table delivers every result row
+ * straight to the GPU that needs it -- the backward exchange (pack + Alltoallv + scatter-add,
+ * arrow_dec_mpi.py:421, 442-475, 437) folded into the epilogue as NVLink stores. */
+int  arrow_ptrtable_upload(arrow_ctx *ctx, const int *bufs, int n_bufs, const int32_t *which, const int64_t *row,
+                           int64_t n, int *table_out);
+int  arrow_ptrtable_free(arrow_ctx *ctx, int table);
+/* Generalised product.  Columns < x_split read X[col], columns >= x_split read X2[col - x_split] (x2_buf < 0: X only):
+ * the feature operand of a level > 0 is [this GPU's level-0 tile | receive region filled by its peers], never
+ * materialised as a tile of its own (forward exchange, arrow_dec_mpi.py:507-550, folded into the column indices).
+ * out_table >= 0: row r is written to table[r] (c_buf may be -1); else to C[r].  add_buf / add_map as arrow_spmm_add. */
+int  arrow_spmm_ex(arrow_ctx *ctx, int csr, int x_buf, int x2_buf, int64_t x_split, int c_buf, int out_table,
+                   int add_buf, int add_map, int variant);
+/* Push: for item i in [item_bounds[d], item_bounds[d+1]):  dst_bufs[d][i - item_bounds[d]] = src[map[i]].
+ * The forward exchange in one pass: local gather, sequential posted stores into each peer's receive region. */
+int  arrow_push_rows(arrow_ctx *ctx, const int *dst_bufs, const int64_t *item_bounds, int n_dst, int src_buf, int map);
+/* out(r) = sum_s src_bufs[s][r] (source order, deterministic) for r < rows; out(r) = table[r] when out_table >= 0 and the
+ * entry is non-null, else dst_buf[r] (dst_buf may be -1: rows without a table entry are skipped).  The reduction of
+ * the partial head tiles (Reduce, arrow_slim_mpi.py:116) in one launch, reading the peers over NVLink. */
+int  arrow_reduce_rows(arrow_ctx *ctx, int dst_buf, int out_table, const int *src_bufs, int n_src, int64_t rows);
+
+/* ---- CUDA graphs: record a whole step once, replay it with one call ------------------------------ */
+/* Between begin and end every launch on the main lane (and on lanes forked from / joined back into it with
+ * arrow_lane_wait) is recorded, not executed.  Run the step once un-captured first (lazy allocations). */
+int  arrow_graph_begin(arrow_ctx *ctx);
+int  arrow_graph_end(arrow_ctx *ctx, int *graph_out);
+int  arrow_graph_launch(arrow_ctx *ctx, int graph);
+int  arrow_graph_free(arrow_ctx *ctx, int graph);
+
 /* ---- cross-process peer memory (one process per GPU; NVLink P2P through CUDA IPC) -------------- */
 /* handle = 64-byte cudaIpcMemHandle_t + 8-byte offset of the tile inside the exported allocation + padding */
 #define ARROW_IPC_HANDLE_BYTES 80
 int  arrow_ipc_export(arrow_ctx *ctx, int buf, void *handle);
 int  arrow_ipc_import(arrow_ctx *ctx, const void *handle, int64_t rows, int k, int *buf_out);
 /* Device-side barrier across `world` ranks over peer-mapped flag words (no host sync, no NCCL):
- * flags_buf[s] is rank s's flag tile (>= world floats... see DESIGN.md), my slot = rank. */
+ * flags_buf[s] is rank s's flag tile (>= world words), my slot = rank.  The epoch counter is device resident (one per
+ * lane), so the launch can be part of a captured graph.  A barrier that waits longer than ARROW_OPT_BARRIER_TIMEOUT_MS
+ * sets a device flag; arrow_sync / arrow_lane_sync then fail and the context refuses further launches. */
 int  arrow_peer_barrier(arrow_ctx *ctx, const int *flag_bufs, int rank, int world);
 
 /* ---- timing (CUDA events on the context's stream) ----------------------------------------------- */

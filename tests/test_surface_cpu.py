@@ -30,7 +30,8 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"libarrow_b200.so does not export {name}"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.arrow_b200_abi_version() == 1
+    header_abi = int(re.search(r"#define ARROW_ABI_VERSION (\d+)", hdr).group(1))
+    assert lib.arrow_b200_abi_version() == header_abi == _lib.ABI_VERSION
 
 
 @pytest.mark.skipif(_cuda(), reason="checks the no-GPU behaviour")
