@@ -122,9 +122,10 @@ struct arrow_ctx {
     int spmm_ctas_per_sm = 0;         // arrow_set_option(ARROW_OPT_SPMM_CTAS_PER_SM): 0 = as many as fit
     int prefetch_plain = 0;           // arrow_set_option(ARROW_OPT_PREFETCH): low nibble = plain launches, high nibble = fused launches;
     int prefetch_fused = 0;           //   0 none, 1 bulk L2 prefetch of the current tile's X rows, 2 of the next tile's (look-ahead)
-    int rows_per_group = 2;           // arrow_set_option(ARROW_OPT_ROWS_PER_GROUP): 2 = paired rows when k <= 32
+    int rows_per_group = 0;           // arrow_set_option(ARROW_OPT_ROWS_PER_GROUP): 0 = auto (pairs at k = 32), 1 / 2 forced
     int spmm_sm_limit = 0;            // arrow_set_option(ARROW_OPT_SPMM_SM_LIMIT): cap on the SMs a SpMM grid covers (0 = all)
     int clock_khz = 2000000;          // SM clock (kHz) for the barrier time-out
+    int smem_carveout = -1;           // arrow_set_option(ARROW_OPT_SMEM_CARVEOUT): preferred shared-memory carve-out (percent) of the tile kernel
     int push_ctas = 0;                // arrow_set_option(ARROW_OPT_PUSH_CTAS): grid of the NVLink push kernel (0 = default)
     long long barrier_timeout_ms = 30000;   // arrow_set_option(ARROW_OPT_BARRIER_TIMEOUT_MS)
     bool poisoned = false;            // a peer barrier timed out: later launches are refused (results would be racy)
@@ -644,7 +645,8 @@ constexpr int TILE_NNZ = 1024;
 constexpr int TILE_ROWS_BIG = 128;  // k <= 32: the panels are small, bigger tiles amortise the per-tile fixed cost
 constexpr int TILE_NNZ_BIG = 2048;
 constexpr int TILE_THREADS = 256;
-constexpr int TILE_STAGES = 3;      // CSR slices in shared memory: tile t (math), t+1 (landed: its X rows are prefetched), t+2 (in flight)
+constexpr int TILE_STAGES = 2;      // CSR slices in shared memory: tile t (math), t+1 (in flight).  A third stage (tried in round 2 for a
+                                    // look-ahead prefetch) cost more L1 than it bought: the L1 data array is the landing buffer of the gathers in flight
 template <int TR, int TN>
 struct TileCfg {
     static constexpr int PTR_WORDS = TR + 8;           // row pointer slice (+ alignment slack)
@@ -665,26 +667,12 @@ struct TileArgs {
     int skip;            // indices may hold -1
     int *ticket;         // dynamic tile scheduler: [0] next tile, [1] CTAs that finished (the last one re-arms both)
     int l2_hints;        // bit 0: X gathers evict_last, bit 1: CSR / C streams evict_first
-    int prefetch;        // 0 none, 1: bulk L2 prefetch of the X rows of the CURRENT tile, 2: of the NEXT tile (look-ahead)
+    int prefetch;        // 1: bulk L2 prefetch of the tile's X rows before the math (A/B switch, off by default)
 };
 
 __device__ __forceinline__ void bulk_prefetch_l2(const void *gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-
 // G lanes own a row (VPL float4 each).  RPG = 2: a group works on two rows at once (rows lr and lr + rows-per-pass) with
 // half the batch size per row: the gathers of both rows are issued before either row's FMAs.  Same registers, but the
 // short tail batch of one row (a 10-entry row is 8 + 2 gathers: the second round trip keeps 2 of 8 slots busy) overlaps
@@ -748,30 +736,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
 #pragma unroll
         for (int s = 0; s < TILE_STAGES; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const int t0 = blockIdx.x;
-        s_tile[0] = t0;
-        int t1 = t.n_tiles;
-        if (t0 < t.n_tiles) {
-            issue_csr(t0, 0);
-            t1 = atomicAdd(t.ticket, 1) + (int)gridDim.x;
-            if (t1 < t.n_tiles) issue_csr(t1, 1);
-        }
-        s_tile[1] = t1;
+        if ((int)blockIdx.x < t.n_tiles) issue_csr(blockIdx.x, 0);
     }
     __syncthreads();
 
     uint32_t phase = 0u;                  // bit s = parity the next wait on stage s expects
     int tile = blockIdx.x;
-    for (int st = 0; tile < t.n_tiles; st = (st + 1 == TILE_STAGES) ? 0 : st + 1) {
+    for (int st = 0; tile < t.n_tiles; st ^= 1) {
         if (threadIdx.x == 0) {
-            const int st1 = (st + 1 == TILE_STAGES) ? 0 : st + 1;
-            const int st2 = (st1 + 1 == TILE_STAGES) ? 0 : st1 + 1;
-            int nn = t.n_tiles;
-            if (s_tile[st1] < t.n_tiles) {
-                nn = atomicAdd(t.ticket, 1) + (int)gridDim.x;
-                if (nn < t.n_tiles) issue_csr(nn, st2);
-            }
-            s_tile[st2] = nn;
+            const int nn = atomicAdd(t.ticket, 1) + (int)gridDim.x;
+            s_tile[st] = nn;
+            if (nn < t.n_tiles) issue_csr(nn, st ^ 1);
         }
         const int4 d = __ldg(t.tiles + tile);
         mbar_wait(&bars[st], (phase >> st) & 1u);
@@ -784,31 +759,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
         const int n_rows_tile = d.y - d.x;
 
         if (t.prefetch) {
-            // Bulk L2 prefetch (one request per X row, issued by the TMA unit, no registers and no LSU wavefronts): either
-            // this tile's rows up front or -- look-ahead -- the rows of the NEXT tile, whose column indices landed in shared
-            // memory one iteration ago.  Puts every first-touch DRAM access of a tile in flight at once; what it buys is
-            // measured in profiles/r02_kernel_sweep.md.
-            int pf_lo = d.z, pf_hi = d.w;
-            const int *pf_idx = s_idx;
-            bool go = true;
-            if (t.prefetch == 2) {
-                const int st1 = (st + 1 == TILE_STAGES) ? 0 : st + 1;
-                const int next = s_tile[st1];
-                go = next < t.n_tiles;
-                if (go) {
-                    const int4 dn = __ldg(t.tiles + next);
-                    mbar_wait(&bars[st1], (phase >> st1) & 1u);         // completed phase: the wait next iteration still passes
-                    pf_lo = dn.z;
-                    pf_hi = dn.w;
-                    pf_idx = stage_base + (size_t)st1 * TILE_STAGE_WORDS + TILE_PTR_WORDS - (dn.z & ~3);
-                }
-            }
-            if (go) {
-                const uint32_t row_bytes = (uint32_t)a.k * 4u;
-                for (int q = pf_lo + (int)threadIdx.x; q < pf_hi; q += TILE_THREADS) {
-                    const int cq = pf_idx[q];
-                    if (cq >= 0) bulk_prefetch_l2(xrow(cq) - gl, row_bytes);
-                }
+            // Bulk L2 prefetch of this tile's X rows (one cp.async.bulk.prefetch.L2 per row, issued by the TMA unit: no
+            // registers, no LSU wavefronts).  Measured in round 2 (profiles/r02_kernel_sweep.md): a LOSS at every k -- the
+            // request rate of the unit, not DRAM latency, becomes the bound.  Off by default; kept as the A/B switch.
+            const uint32_t row_bytes = (uint32_t)a.k * 4u;
+            for (int q = d.z + (int)threadIdx.x; q < d.w; q += TILE_THREADS) {
+                const int cq = s_idx[q];
+                if (cq >= 0) bulk_prefetch_l2(xrow(cq) - gl, row_bytes);
             }
         }
 
@@ -841,6 +798,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
                     } else {
                         cr[r] = Cl + row * k4;
                     }
+                }
+                if constexpr (NR == 1) {
+                    if (!live[0]) return;               // one row per group: nothing to keep predicated past this point
+                    live[0] = true;
                 }
                 // accumulate mode: the old C row is read FIRST so that its latency hides behind the gathers (only this
                 // group ever touches the row: the row maps are injective)
@@ -949,7 +910,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
                     float4 x[TAIL][VPL];
 #pragma unroll
                     for (int u = 0; u < TAIL; ++u) {
-                        const float4 *xr = xrow(c[u] >= 0 ? c[u] : 0);
+                        const float4 *xr = xrow(c[u]);                    // c = -1: address arithmetic only, never dereferenced
 #pragma unroll
                         for (int i = 0; i < VPL; ++i)
                             x[u][i] = (c[u] >= 0 && gl + i * G < k4) ? ldg_f4_hint(xr + i * G, pol_keep) : f4_zero();
@@ -980,7 +941,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles(TileArgs t) {
             for (int lr = warp * RPW + gi; lr < n_rows_tile; lr += ROWS_PER_PASS) do_rows(std::integral_constant<int, 1>{}, lr);
         }
         __syncthreads();            // stage `st` may be refilled by the next iteration's CSR copy
-        tile = s_tile[(st + 1 == TILE_STAGES) ? 0 : st + 1];
+        tile = s_tile[st];
     }
     // the last CTA to leave re-arms the scheduler for the next launch on this lane (no memset between launches)
     if (threadIdx.x == 0) {
@@ -1292,12 +1253,16 @@ __global__ void k_map_from_i64(const long long *__restrict__ in, int *__restrict
 }
 
 __global__ void k_remap(const int *__restrict__ idx, const int *__restrict__ map, long long map_n, int *__restrict__ out,
-                        long long n) {
+                        long long n, int *any_invalid) {
     const long long stride = (long long)gridDim.x * blockDim.x;
+    bool bad = false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int c = idx[i];
-        out[i] = (c < 0 || c >= map_n) ? -1 : map[c];
+        const int m = (c < 0 || c >= map_n) ? -1 : map[c];
+        out[i] = m;
+        bad = bad || m < 0;
     }
+    if (bad && any_invalid != nullptr) atomicExch(any_invalid, 1);
 }
 
 __global__ void k_map_invert(const int *__restrict__ map, long long n, int *__restrict__ out, long long n_out) {
@@ -1422,6 +1387,11 @@ int launch_tiles_one(arrow_ctx *ctx, const TileArgs &t) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[dv], fn, TILE_THREADS, SMEM) != cudaSuccess || occ_dev[dv] < 1) occ_dev[dv] = 1;
         attr_set[dv] = true;
     }
+    static int carve_dev[64];
+    if (ctx->smem_carveout != carve_dev[dv] - 1000) {       // measurement switch: how much of the 228 KB is L1
+        cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, ctx->smem_carveout);
+        carve_dev[dv] = ctx->smem_carveout + 1000;
+    }
     const int occ = occ_dev[dv];
     const int per_sm = (ctx->spmm_ctas_per_sm > 0) ? std::min(occ, ctx->spmm_ctas_per_sm) : occ;
     int sms = ctx->sm_count;
@@ -1470,7 +1440,8 @@ int launch_tiles(arrow_ctx *ctx, TileArgs &t, const Csr *A, const TileLaunch &L)
     while (g < lanes) g <<= 1;
     const bool big = (k4 <= 8) && ctx->big_tiles && A->n_tiles_big > 0;     // k <= 32
     if (big) { t.tiles = A->tiles_big; t.n_tiles = A->n_tiles_big; }
-    int rpg = L.rpg_req ? L.rpg_req : ctx->rows_per_group;
+    // measured at 10M rows (profiles/r02_kernel_sweep.md): pairs win at k = 32 (+3.5 %), lose at k = 16 (-10 %)
+    int rpg = L.rpg_req ? L.rpg_req : (ctx->rows_per_group ? ctx->rows_per_group : (vpl == 2 ? 2 : 1));
     if (!big || rpg != 2) rpg = 1;                                           // pairs need >= 2 passes per tile
 #define TL(GG, VV)                                                                                       \
     if (g == GG && vpl == VV) return launch_tiles_gv<GG, VV, TILE_ROWS, TILE_NNZ, 1, 4>(ctx, t, L)
@@ -1631,9 +1602,10 @@ int arrow_set_option(arrow_ctx *ctx, int option, int value) {
         case ARROW_OPT_BIG_TILES: ctx->big_tiles = value ? 1 : 0; return ARROW_OK;
         case ARROW_OPT_SPMM_CTAS_PER_SM: ctx->spmm_ctas_per_sm = value < 0 ? 0 : value; return ARROW_OK;
         case ARROW_OPT_PREFETCH: ctx->prefetch_plain = value & 0xF; ctx->prefetch_fused = (value >> 4) & 0xF;
-            if (ctx->prefetch_plain > 2 || ctx->prefetch_fused > 2) { ctx->prefetch_plain = ctx->prefetch_fused = 0; return fail(ctx, ARROW_ERR_ARG, "prefetch modes are 0..2 per nibble"); }
+            if (ctx->prefetch_plain > 1 || ctx->prefetch_fused > 1) { ctx->prefetch_plain = ctx->prefetch_fused = 0; return fail(ctx, ARROW_ERR_ARG, "prefetch modes are 0..1 per nibble"); }
             return ARROW_OK;
-        case ARROW_OPT_ROWS_PER_GROUP: ctx->rows_per_group = (value == 2) ? 2 : 1; return ARROW_OK;
+        case ARROW_OPT_ROWS_PER_GROUP: ctx->rows_per_group = (value == 1 || value == 2) ? value : 0; return ARROW_OK;
+        case ARROW_OPT_SMEM_CARVEOUT: ctx->smem_carveout = value; return ARROW_OK;
         case ARROW_OPT_SPMM_SM_LIMIT: ctx->spmm_sm_limit = value < 0 ? 0 : value; return ARROW_OK;
         case ARROW_OPT_PUSH_CTAS: ctx->push_ctas = value < 0 ? 0 : value; return ARROW_OK;
         case ARROW_OPT_BARRIER_TIMEOUT_MS: ctx->barrier_timeout_ms = value < 1 ? 1 : value; return ARROW_OK;
@@ -1843,20 +1815,30 @@ int arrow_csr_remap_columns(arrow_ctx *ctx, int csr, int map, int64_t new_n_cols
     d.owns_indices = true;
     d.indices = nullptr;
     d.n_cols = new_n_cols;
-    d.may_skip = true;
     d.parent = csr;
     d.children = 0;
     CUDA_TRY(ctx, cudaMalloc(&d.indices, ((size_t)c->nnz + 8) * sizeof(int)));
     cudaError_t e = cudaMemsetAsync(d.indices, 0, ((size_t)c->nnz + 8) * sizeof(int), ctx->stream);
+    int h_invalid = 0;
     if (e == cudaSuccess && c->nnz > 0) {
-        k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->indices, m->p, m->n, d.indices, c->nnz);
-        ctx->launches++;
-        e = cudaGetLastError();
+        DevTmp flag;
+        e = cudaMalloc(&flag.p, sizeof(int));
+        if (e == cudaSuccess) e = cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream);
+        if (e == cudaSuccess) {
+            k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(c->indices, m->p, m->n, d.indices, c->nnz, (int *)flag.p);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h_invalid, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
     if (e != cudaSuccess) {
         cudaFree(d.indices);
         return fail(ctx, ARROW_ERR_CUDA, "column remap failed: %s", cudaGetErrorString(e));
     }
+    // entries whose image is invalid are skipped by the kernels (predicated gathers); when every entry maps to a valid
+    // column -- always the case on the fused path -- the copy runs the unpredicated batches like its source
+    d.may_skip = c->may_skip || h_invalid != 0;
     const int h = new_slot(ctx->csrs);       // may grow the table: `c` is not used past this point
     ctx->csrs[h] = d;
     ctx->csrs[csr].children++;
@@ -1918,7 +1900,7 @@ int arrow_map_compose(arrow_ctx *ctx, int inner, int outer, int *map_out) {
     m.limit = b->limit;
     CUDA_TRY(ctx, cudaMalloc(&m.p, (size_t)std::max<int64_t>(m.n, 1) * sizeof(int)));
     if (m.n > 0) {
-        k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a->p, b->p, b->n, m.p, m.n);
+        k_remap<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(a->p, b->p, b->n, m.p, m.n, nullptr);
         ctx->launches++;
     }
     if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {

@@ -49,7 +49,7 @@ typedef struct arrow_ctx arrow_ctx;
 #define ARROW_VARIANT_SHFL     1  /* sub-warp per row, coalesced index/value chunk + shuffle broadcast  */
 #define ARROW_VARIANT_TMA      2  /* X rows staged into shared memory with cp.async.bulk + mbarrier     */
 #define ARROW_VARIANT_TILES    3  /* default: CSR row tiles streamed by cp.async.bulk (TMA) + mbarrier,
-                                     three stages; warps only issue X gathers.  Bits 4..7 of `variant`
+                                     two stages; warps only issue X gathers.  Bits 4..7 of `variant`
                                      optionally force the float4-per-lane count (1, 2 or 4), bits 8..9 the
                                      rows a lane group works on at once (1 or 2; 2 needs k <= 32).     */
 
@@ -69,15 +69,17 @@ int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segme
 #define ARROW_OPT_L2_HINTS_PLAIN 1
 #define ARROW_OPT_L2_HINTS_FUSED 2
 #define ARROW_OPT_BIG_TILES      3   /* 1 (default): 128-row / 2048-entry CSR tiles when k <= 32 */
-#define ARROW_OPT_PREFETCH        5   /* bulk L2 prefetch (cp.async.bulk.prefetch.L2, one request per X row) issued per CSR tile:
-                                        low nibble = plain launches, high nibble = fused launches (row map / accumulate /
-                                        gather-add / dual X / row pointers); 0 none, 1 = the current tile's rows, 2 = the next
-                                        tile's rows (look-ahead) */
+#define ARROW_OPT_PREFETCH        5   /* bulk L2 prefetch (cp.async.bulk.prefetch.L2, one request per X row) of a CSR tile's X rows
+                                        before its math: bit 0 = plain launches, bit 4 = fused launches (row map / accumulate /
+                                        gather-add / dual X / row pointers).  Measured as a loss (profiles/r02_kernel_sweep.md);
+                                        off by default, kept as the A/B switch */
 #define ARROW_OPT_SPMM_CTAS_PER_SM 4 /* cap on resident SpMM CTAs per SM (0 = no cap): leaves SM resources to exchange
                                         kernels running on the side lane */
-#define ARROW_OPT_ROWS_PER_GROUP  6   /* 2 (default): a lane group gathers for two rows at once when k <= 32; 1: one row */
+#define ARROW_OPT_ROWS_PER_GROUP  6   /* rows a lane group gathers for at once when k <= 32: 0 (default) = auto (2 at k = 32, else 1), 1, 2 */
 #define ARROW_OPT_SPMM_SM_LIMIT   7   /* cap on the SMs a SpMM grid covers (0 = all): concurrent launches on two lanes share the GPU */
 #define ARROW_OPT_PUSH_CTAS       8   /* grid of arrow_push_rows (0 = 2 per SM) */
+#define ARROW_OPT_SMEM_CARVEOUT  10   /* preferred shared-memory carve-out (percent, -1 = driver default) of the tile kernel: the rest of
+                                        the SM's 228 KB is L1, the landing buffer of the gathers in flight (measurement switch) */
 #define ARROW_OPT_BARRIER_TIMEOUT_MS 9 /* arrow_peer_barrier gives up after this long (default 30000) and poisons the context */
 int  arrow_set_option(arrow_ctx *ctx, int option, int value);
 

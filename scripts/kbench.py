@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--peak", type=float, default=0.0)
     ap.add_argument("--big-tiles", type=int, default=1)
     ap.add_argument("--prefetch", type=str, default="0", help="comma list of ARROW_OPT_PREFETCH values to sweep (low nibble = plain launches)")
+    ap.add_argument("--carveout", type=str, default="-1", help="comma list of ARROW_OPT_SMEM_CARVEOUT values (percent; -1 = driver default)")
     ap.add_argument("--no-flush", action="store_true", help="skip the flushed timing (inputs far larger than L2)")
     args = ap.parse_args()
 
@@ -64,12 +65,14 @@ def main():
         dX, dC = ctx.dense_from_host(X), ctx.dense_alloc(n, k)
         alg_bytes = A.nnz * 8 + (n + 1) * 4 + 2.0 * n * k * 4
         flops = 2.0 * A.nnz * k
-        for v, pf in [(int(x), int(q)) for x in args.variants.split(",") for q in args.prefetch.split(",")]:
+        for v, pf, cv in [(int(x), int(q), int(c)) for x in args.variants.split(",") for q in args.prefetch.split(",")
+                          for c in args.carveout.split(",")]:
             if (v & 0xF) == 2 and (k < 32 or k > 128):
                 continue
             if (v >> 8) == 2 and k > 32:
                 continue
             ctx.set_option(ctx.OPT_PREFETCH, pf)
+            ctx.set_option(ctx.OPT_SMEM_CARVEOUT, cv)
             for _ in range(3):
                 ctx.spmm(dA, dX, dC, variant=v)
             times = []
@@ -87,7 +90,7 @@ def main():
             ctx.timer_stop(2)
             warm = ctx.timer_ms(2) / args.iters
             med = float(np.median(times))
-            print(json.dumps({"k": k, "variant": v, "rpg": (v >> 8) & 3, "vpl": (v >> 4) & 15, "prefetch": pf, "rows": n, "ms_flushed": round(med, 4), "ms_min": round(min(times), 4),
+            print(json.dumps({"k": k, "variant": v, "rpg": (v >> 8) & 3, "vpl": (v >> 4) & 15, "prefetch": pf, "carveout": cv, "big_tiles": args.big_tiles, "rows": n, "ms_flushed": round(med, 4), "ms_min": round(min(times), 4),
                               "ms_back_to_back": round(warm, 4), "alg_GBps": round(alg_bytes / med / 1e6, 1),
                               "frac_of_peak": round(alg_bytes / med / 1e6 / peak, 3), "GFLOPs": round(flops / med / 1e6, 1),
                               "alg_MB": round(alg_bytes / 1e6, 1)}), flush=True)
