@@ -43,7 +43,7 @@ class ArrowDecompositionMPI:
 
     def __init__(self, comm, B: ArrowSlimMPI, matrix_index: int, number_of_rows_per_rank: int,
                  number_of_feature_columns: int, groups, to_previous_permutation, to_next_mapping,
-                 device='gpu', slim=True, block_diagonal=True, n_blocks=None, mode="auto", exchange="p2p"):
+                 device='gpu', slim=True, block_diagonal=True, n_blocks=None, mode="auto", exchange="p2p", overlap=1):
         _require_gpu(device)
         self.comm = comm
         self.B = B
@@ -59,6 +59,7 @@ class ArrowDecompositionMPI:
         self._to_next = to_next_mapping
         self._mode = mode
         self._exchange = exchange
+        self._overlap = overlap
         self._engine = None
         self.levels: List[ArrowSlimMPI] = [B]
         B._owner = self
@@ -67,7 +68,7 @@ class ArrowDecompositionMPI:
     @staticmethod
     def initialize(comm, n_blocks: np.ndarray, to_prev_permutation, to_next_permutation, rows_per_rank: int,
                    feature_columns: int, device='gpu', block_diagonal: bool = True, slim: bool = False, mode: str = "auto",
-                   exchange: str = "p2p"):
+                   exchange: str = "p2p", overlap: int = 1):
         """Same arguments as the reference (``:106-115``).  ``slim`` only selects the reference's rank
         layout; on a GPU both layouts are the same row-partitioned kernels, so it is accepted and ignored."""
         assert not slim or block_diagonal
@@ -77,7 +78,7 @@ class ArrowDecompositionMPI:
         B = level_operator(None, 0)
         arrow = ArrowDecompositionMPI(comm, B, 0, rows_per_rank, feature_columns, None, to_prev_permutation,
                                       to_next_permutation, device=device, slim=slim, block_diagonal=block_diagonal,
-                                      n_blocks=[int(b) for b in n_blocks], mode=mode, exchange=exchange)
+                                      n_blocks=[int(b) for b in n_blocks], mode=mode, exchange=exchange, overlap=overlap)
         arrow.levels = [B] + [level_operator(arrow, j) for j in range(1, len(n_blocks))]
         return arrow
 
@@ -92,13 +93,15 @@ class ArrowDecompositionMPI:
             # one process per GPU: this rank's block-rows of every level, straight from the memory maps
             import os
             from .sharded import CudaPeerBackend, NcclBackend, ShardPlan, ShardedArrowEngine
-            dev = int(os.environ.get("LOCAL_RANK", self.comm.Get_rank()))
+            dev = getattr(self.comm, "device", None)
+            if dev is None:
+                dev = int(os.environ.get("LOCAL_RANK", self.comm.Get_rank()))
             plan = ShardPlan(blocks.decomposition, blocks.width, self.comm.Get_rank(), self.comm.Get_size(),
                              block_diagonal=blocks.block_diagonal, n_blocks=self.n_blocks)
             be = NcclBackend(self.comm, dev, blocks.width, plan) if self._exchange == "nccl" \
                 else CudaPeerBackend(self.comm, dev, blocks.width, plan=None if self._exchange == "p2p-direct" else plan)
             be.layout_plan = plan
-            self._engine = ShardedArrowEngine(plan, self._n_feature_columns, be)
+            self._engine = ShardedArrowEngine(plan, self._n_feature_columns, be, overlap=self._overlap, mode=self._mode)
         else:
             self._engine = ArrowEngine(blocks.decomposition, blocks.width, self._n_feature_columns,
                                        block_diagonal=blocks.block_diagonal, mode=self._mode, n_blocks=self.n_blocks,
@@ -134,11 +137,8 @@ class ArrowDecompositionMPI:
     def step_stream(self, X_host: np.ndarray, out_host: np.ndarray):
         """Extension for host-resident features: enqueue ``set_features(X); step(); result_tile(out)`` so that
         uploads, compute and downloads of consecutive iterations overlap (see ``ArrowEngine.stream_step``).
-        Call ``synchronize()`` before reading ``out_host``.  Single-GPU engine only."""
-        eng = self._require_engine()
-        if not hasattr(eng, "stream_step"):
-            raise NotImplementedError("step_stream is implemented for the single-GPU engine")
-        eng.stream_step(X_host, out_host)
+        Call ``synchronize()`` before reading ``out_host``.  On N GPUs every rank passes its own rows."""
+        self._require_engine().stream_step(X_host, out_host)
 
     def synchronize(self):
         self._require_engine().sync()

@@ -78,6 +78,61 @@ class TorchComm:
         return [row[me] for row in self.allgather(list(objs))]
 
 
+class ThreadWorld:
+    """Shared state of ``n`` ranks that live as threads of ONE process (``ThreadComm``): the engine then needs no CUDA IPC --
+    peers' tiles are plain pointers of the same address space.  Used to drive several rank engines on a single GPU
+    (the multi-rank tests on a one-GPU box) and usable for one process driving all GPUs of a box."""
+
+    def __init__(self, n: int, devices=None):
+        import threading
+        self.n = int(n)
+        self.devices = [0] * self.n if devices is None else [int(d) for d in devices]
+        self._barrier = threading.Barrier(self.n)
+        self._slots: List[Any] = [None] * self.n
+
+    def comm(self, rank: int) -> "ThreadComm":
+        return ThreadComm(self, rank)
+
+
+class ThreadComm:
+    def __init__(self, world: ThreadWorld, rank: int):
+        self._w, self._rank = world, int(rank)
+        self.device = world.devices[self._rank]          # the CUDA device this rank drives
+
+    def Get_rank(self) -> int:
+        return self._rank
+
+    def Get_size(self) -> int:
+        return self._w.n
+
+    rank = property(Get_rank)
+    size = property(Get_size)
+
+    def Barrier(self) -> None:
+        self._w._barrier.wait()
+
+    def allgather(self, obj: Any) -> List[Any]:
+        w = self._w
+        w._slots[self._rank] = obj
+        w._barrier.wait()
+        out = list(w._slots)
+        w._barrier.wait()               # nobody overwrites a slot before everyone has read it
+        return out
+
+    def allreduce_lor(self, flag: bool) -> bool:
+        return any(self.allgather(bool(flag)))
+
+    def bcast(self, obj: Any, root: int = 0) -> Any:
+        return self.allgather(obj if self._rank == root else None)[root]
+
+    def alltoall(self, objs: List[Any]) -> List[Any]:
+        return [row[self._rank] for row in self.allgather(list(objs))]
+
+    def abort(self) -> None:
+        """wake every rank blocked in a collective (a failing rank calls this so that its peers fail instead of hanging)"""
+        self._w._barrier.abort()
+
+
 def init_from_env() -> None:
     """Under ``torchrun`` (WORLD_SIZE > 1) bring up torch.distributed: NCCL with one GPU per process when CUDA is
     there, gloo otherwise.  The reference gets its world from ``mpiexec`` + ``MPI.COMM_WORLD`` instead."""

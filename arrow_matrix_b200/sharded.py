@@ -182,6 +182,69 @@ class ShardPlan:
     def own_bounds(self, level: int) -> np.ndarray:
         return self.levels[level].bounds
 
+    # -- layouts of OTHER ranks (every rank derives the whole routing from the global maps: no set-up traffic) ----
+    def layout_of(self, level: int, g: int):
+        """``(head_rows, halo_prev_off, hoff, halo_next_off, local_rows, r0, r1)`` of rank ``g`` at ``level``"""
+        w = self.width
+        bounds = self.levels[level].bounds
+        nb = self.n_blocks[level]
+        r0, r1 = int(bounds[g]), int(bounds[g + 1])
+        prev, nxt = self._halo_flags(bounds, nb, g)
+        head = w if g > 0 else 0
+        hoff = head + (w if prev else 0)
+        own = r1 - r0
+        return head, (head if prev else -1), hoff, (hoff + own if nxt else -1), hoff + own + (w if nxt else 0), r0, r1
+
+    def local_to_global(self, level: int, g: int) -> np.ndarray:
+        """global row of ``level`` held by every row of rank ``g``'s local tile: [head | halo_prev | own | halo_next]"""
+        w = self.width
+        head, prev_off, hoff, next_off, local_rows, r0, r1 = self.layout_of(level, g)
+        out = np.empty(local_rows, dtype=np.int64)
+        if head:
+            out[:w] = np.arange(w, dtype=np.int64)
+        if prev_off >= 0:
+            out[prev_off:prev_off + w] = np.arange(r0 - w, r0, dtype=np.int64)
+        out[hoff:hoff + (r1 - r0)] = np.arange(r0, r1, dtype=np.int64)
+        if next_off >= 0:
+            out[next_off:next_off + w] = np.arange(r1, r1 + w, dtype=np.int64)
+        return out
+
+    def local_index(self, level: int, g: int, rows: np.ndarray) -> np.ndarray:
+        """position of global ``rows`` of ``level`` inside rank ``g``'s local tile, -1 where ``g`` does not hold the row"""
+        w = self.width
+        head, prev_off, hoff, next_off, _, r0, r1 = self.layout_of(level, g)
+        rows = np.asarray(rows, dtype=np.int64)
+        out = np.full(rows.shape, -1, dtype=np.int64)
+        if head:
+            m = (rows >= 0) & (rows < w)
+            out[m] = rows[m]
+        if prev_off >= 0:
+            m = (rows >= r0 - w) & (rows < r0)
+            out[m] = rows[m] - (r0 - w) + prev_off
+        if next_off >= 0:
+            m = (rows >= r1) & (rows < r1 + w)
+            out[m] = rows[m] - r1 + next_off
+        m = (rows >= r0) & (rows < r1)
+        out[m] = rows[m] - r0 + hoff
+        return out
+
+    def composed_maps(self) -> List[Optional[np.ndarray]]:
+        """``cmap[j][r]`` = row of level 0 that feeds row ``r`` of level ``j`` (``to_prev`` chained down), -1 when the chain
+        leaves the active rows of some level (the reference's sentinel, arrow_dec_mpi.py:740-749)"""
+        if getattr(self, "_cmap", None) is None:
+            cmap: List[Optional[np.ndarray]] = [None]
+            prev = None
+            for j in range(1, self.L):
+                rows_j, rows_p = self.levels[j].rows_global, self.levels[j - 1].rows_global
+                tp = self.to_prev[j][:rows_j]
+                valid = tp < rows_p
+                safe = np.where(valid, tp, 0)
+                cur = np.where(valid, safe if prev is None else prev[safe], -1)
+                cmap.append(cur)
+                prev = cur
+            self._cmap = cmap
+        return self._cmap
+
     def a2a_tables(self, dst_level: int, forward: bool):
         """Pack / unpack tables of one level exchange for an all-to-all-v (the NCCL backend).
 
@@ -214,23 +277,161 @@ class ShardPlan:
         return dict(pack=pack.astype(np.int64), send_counts=send_counts, recv_counts=recv_counts, unpack=unpack)
 
 
+class FusedPlan:
+    """Routing of the fused multi-GPU step for one rank (pure numpy, derived from the global maps on every rank).
+
+    Forward: the feature operand of level ``j >= 1`` on this GPU is never materialised.  Column ``c`` of the local level
+    matrix stands for the level-``j`` row ``g``; its value is row ``cmap_j[g]`` of level 0.  If this GPU holds that
+    level-0 row (own rows, head tile, halo) the column index points into the level-0 tile, otherwise into the
+    *receive region*: one slot per remote row, grouped by source GPU, which the owners fill with ONE push kernel
+    (``arrow_push_rows``) per step.  ``colmap[j]`` is that re-indexing; columns ``>= x_split`` address the region.
+
+    Backward: ``C_{j-1}[to_prev_j[g]] += C_j[g]`` (arrow_dec_mpi.py:437).  Every row of level ``j-1`` that receives a
+    contribution has one slot in its owner's *staging tile*; the level-``j`` SpMM writes each result row straight into
+    the slot (``out_which/out_row``: a pointer table, local or over NVLink), and level ``j-1`` adds its staging tile in
+    its own epilogue (``add_map``; level 0: one final gather-add).  Head rows (block-row 0 is computed as partial sums
+    by every GPU) stay local, are reduced by GPU 0 and delivered by the reduction kernel (``head_which/head_row``).
+    """
+
+    def __init__(self, plan: "ShardPlan"):
+        self.plan = plan
+        pl, me, world, w, L = plan, plan.rank, plan.world, plan.width, plan.L
+        cmap = pl.composed_maps()
+        b0 = pl.levels[0].bounds
+        self.x_split = pl.levels[0].local_rows
+        # ---- forward: what every destination needs, in its slot order -----------------------------------------
+        self.colmap: List[Optional[np.ndarray]] = [None] * L
+        self.ok = True
+        push_src, push_bounds, push_off = [], [0], []
+        self.recv_rows = 0
+        for d in range(world):
+            glob_all, lvl_all, lc_all, src_all = [], [], [], []
+            for j in range(1, L):
+                glob = pl.local_to_global(j, d)
+                inside = glob < pl.levels[j].rows_global
+                src0 = np.where(inside, cmap[j][np.where(inside, glob, 0)], -1)
+                glob_all.append(glob); src_all.append(src0)
+                lvl_all.append(np.full(glob.size, j, dtype=np.int64)); lc_all.append(np.arange(glob.size, dtype=np.int64))
+            if not src_all:                                                # a single level: nothing is exchanged
+                push_off.append(0)
+                push_bounds.append(push_bounds[-1])
+                continue
+            src0 = np.concatenate(src_all)
+            loc = pl.local_index(0, d, src0)
+            remote = (src0 >= 0) & (loc < 0)
+            owner = np.searchsorted(b0, np.where(remote, src0, 0), side="right") - 1
+            ridx = np.flatnonzero(remote)
+            order = ridx[np.argsort(owner[ridx], kind="stable")]          # slot order: (source rank, level, local column)
+            counts = np.bincount(owner[order], minlength=world).astype(np.int64)
+            offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            if d == me:
+                slot = np.full(src0.size, -1, dtype=np.int64)
+                slot[order] = np.arange(order.size, dtype=np.int64)
+                self.recv_rows = int(order.size)
+                self.recv_counts = counts
+                pos = 0
+                for j in range(1, L):
+                    n = src_all[j - 1].size
+                    cm = np.where(loc[pos:pos + n] >= 0, loc[pos:pos + n],
+                                  np.where(slot[pos:pos + n] >= 0, self.x_split + slot[pos:pos + n], -1))
+                    self.colmap[j] = cm
+                    idx = pl.levels[j].indices
+                    if idx.size and np.any(cm[idx] < 0):
+                        self.ok = False                    # a non-zero reads a row behind the sentinel: exchange mode only
+                    pos += n
+                push_off.append(0)
+            else:
+                mine = order[owner[order] == me]                           # d's slots that I fill, in d's slot order
+                push_src.append(pl.local_index(0, me, src0[mine]))
+                push_bounds.append(push_bounds[-1] + mine.size)
+                push_off.append(int(offs[me]))                             # where my rows start inside d's region
+                continue
+            push_bounds.append(push_bounds[-1])
+        self.push_src = np.concatenate(push_src) if push_src else np.zeros(0, dtype=np.int64)
+        self.push_bounds = np.asarray(push_bounds, dtype=np.int64)         # world + 1 entries (my own slice is empty)
+        self.push_off = push_off
+        assert self.push_src.size == 0 or self.push_src.min() >= 0
+        # ---- backward: staging slots of every level that receives --------------------------------------------
+        self.stage_rows = [0] * max(L - 1, 0)                              # my staging tile of level j (filled by level j+1)
+        self.add_map: List[Optional[np.ndarray]] = [None] * L              # local row of level j -> slot in my staging tile
+        self.out_which: List[Optional[np.ndarray]] = [None] * L            # level j >= 1: 0 = local C tile, 1+d = staging tile of d
+        self.out_row: List[Optional[np.ndarray]] = [None] * L
+        self.head_which: List[Optional[np.ndarray]] = [None] * L           # GPU 0 only: where the reduced head rows go
+        self.head_row: List[Optional[np.ndarray]] = [None] * L
+        for j in range(1, L):
+            rows_j, rows_p = pl.levels[j].rows_global, pl.levels[j - 1].rows_global
+            bp = pl.levels[j - 1].bounds
+            tn = pl.to_next[j - 1][:rows_p]
+            receives = tn < rows_j                                         # rows of level j-1 that get a contribution
+            before = np.concatenate([[0], np.cumsum(receives)]).astype(np.int64)
+            shp = pl.levels[j - 1]
+            self.stage_rows[j - 1] = int(before[shp.r1] - before[shp.r0])
+            am = np.full(shp.local_rows, -1, dtype=np.int64)
+            own = np.arange(shp.r0, shp.r1, dtype=np.int64)
+            am[shp.hoff:shp.hoff + own.size] = np.where(receives[own], before[own] - before[shp.r0], -1)
+            self.add_map[j - 1] = am
+
+            def route(g):
+                """(which, row) of level-j rows ``g``: the staging slot at the owner of to_prev_j[g]"""
+                tp = pl.to_prev[j][g]
+                valid = tp < rows_p
+                tps = np.where(valid, tp, 0)
+                dst = np.searchsorted(bp, tps, side="right") - 1
+                return np.where(valid, 1 + dst, -1).astype(np.int32), np.where(valid, before[tps] - before[bp[dst]], 0)
+
+            sh = pl.levels[j]
+            which = np.full(sh.local_rows, -1, dtype=np.int32)
+            row = np.zeros(sh.local_rows, dtype=np.int64)
+            hr = min(w, rows_j)
+            if me > 0:                                                     # partial head rows stay local (reduced by GPU 0)
+                which[:hr] = 0
+                row[:hr] = np.arange(hr)
+            g = np.arange(sh.r0, sh.r1, dtype=np.int64)
+            if g.size:
+                wq, rq = route(g)
+                part = g < hr                                              # GPU 0's own share of block-row 0: a partial sum too
+                wq = np.where(part, 0, wq)
+                rq = np.where(part, sh.hoff + (g - sh.r0), rq)
+                which[sh.hoff:sh.hoff + g.size] = wq
+                row[sh.hoff:sh.hoff + g.size] = rq
+            self.out_which[j], self.out_row[j] = which, row
+            if me == 0:
+                self.head_which[j], self.head_row[j] = route(np.arange(hr, dtype=np.int64))
+
+
 # ------------------------------------------------------------------------------------------------------
 # engine
 # ------------------------------------------------------------------------------------------------------
 class ShardedArrowEngine:
     """Executes a ShardPlan.  ``backend`` supplies device memory, kernels, peer access and barriers."""
 
-    def __init__(self, plan: ShardPlan, k: int, backend, overlap: bool = False, split_frac: float = 0.5):
+    def __init__(self, plan: ShardPlan, k: int, backend, overlap: bool = False, split_frac: float = 0.5, mode: str = "auto"):
+        """``mode``: 'fused' (push exchange folded into the SpMMs, see ``FusedPlan``), 'exchange' (the literal protocol with
+        every level's tiles materialised: needed when a non-zero reads a row behind the sentinel, and for
+        ``result(level > 0)``), 'auto' = fused when it is exact and the backend can push."""
+        if mode not in ("auto", "fused", "exchange"):
+            raise ValueError(f"mode must be auto|fused|exchange, got {mode!r}")
         self.plan, self.k, self.be = plan, int(k), backend
         self.overlap = bool(overlap) and hasattr(backend, "side_begin")
         self.overlap_ctas = 3
+        self.rank, self.world, self.width, self.L = plan.rank, plan.world, plan.width, plan.L
+        be = backend
+        # fused step: every rank checks its own level matrices against its routing, all ranks agree
+        self.fp = None
+        if mode != "exchange" and self.L >= 2 and getattr(backend, "supports_fused", False):
+            fp = FusedPlan(plan)
+            if int(be.allreduce_sum(0 if fp.ok else 1)) == 0:
+                self.fp = fp
+        if mode == "fused" and self.fp is None:
+            raise ValueError("fused mode requested but a level reads rows behind the sentinel (or the backend cannot push); "
+                             "use mode='exchange'")
+        self.fused_ok = self.fp is not None
         # overlap=2 (two levels, staged exchange available): level 0 is multiplied in two row parts so that BOTH
         # exchanges hide behind it -- forward behind part a, backward (staged into a buffer) behind part b
-        self.split = (self.overlap and int(overlap) == 2 and plan.L == 2 and plan.world > 1
+        self.split = (self.fp is None and self.overlap and int(overlap) == 2 and plan.L == 2 and plan.world > 1
                       and getattr(backend, "supports_staged_exchange", False))
-        self.rank, self.world, self.width, self.L = plan.rank, plan.world, plan.width, plan.L
-        self.mode = "exchange-" + type(backend).__name__
-        be = backend
+        self.mode = ("fused-" if self.fp is not None else "exchange-") + type(backend).__name__
+        self.graphs = {}
         self.mats, self.fwd, self.bwd = [], [], []
         for sh in plan.levels:
             self.mats.append(be.csr_upload(sh.local_rows, sh.local_rows, sh.indptr, sh.indices, sh.data)
@@ -259,7 +460,20 @@ class ShardedArrowEngine:
                 a, b = int(ip[r0]), int(ip[r1])
                 self._parts.append(be.csr_upload(r1 - r0, sh0.local_rows, ip[r0:r1 + 1] - a, sh0.indices[a:b], sh0.data[a:b])
                                    if r1 > r0 else None)
+        if self.fp is not None:
+            # two more kinds of shared tiles: the receive region of the forward push and one staging tile per level
+            # that receives contributions from the level below it
+            self._recv = (len(rows_per_level), 0)
+            rows_per_level.append(max(self.fp.recv_rows, 1))
+            tiles_per_level.append(1)
+            self._stg = []
+            for j in range(self.L - 1):
+                self._stg.append((len(rows_per_level), 0))
+                rows_per_level.append(max(self.fp.stage_rows[j], 1))
+                tiles_per_level.append(1)
         self.tiles = be.alloc_shared_tiles(rows_per_level, self.k, tiles_per_level=tiles_per_level)
+        if self.fp is not None:
+            self._setup_fused()
         self.xi = [0] * self.L
         self.ci = [0] * self.L
         self._pair = 0                      # which level-0 pair is active: tile index = 2*pair + {0,1}
@@ -318,6 +532,8 @@ class ShardedArrowEngine:
         ctx.lane_sync(2)
 
     def result(self, level: int = 0, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if level > 0 and self.fp is not None:
+            raise RuntimeError("levels > 0 are not materialised by the fused step; construct with mode='exchange'")
         sh = self.plan.levels[level]
         return self.be.d2h(self.tiles[level][self.ci[level]], sh.hoff, sh.own_rows, out)
 
@@ -356,7 +572,11 @@ class ShardedArrowEngine:
         be.barrier()
 
     def ensure_level_tiles(self):
-        pass                                                    # the sharded engine always materialises them
+        """Per-level tiles exist in both modes; the fused step just never fills levels > 0 -- callers that want them
+        (``result(level > 0)``, the phase-by-phase ``_propagate_features`` / ``_aggregate`` surface) get the literal protocol."""
+        if self.fp is not None:
+            self.fp = None
+            self.mode = "exchange-" + type(self.be).__name__
 
     def sync(self):
         if getattr(self.be, "ctx", None) is not None:
@@ -472,7 +692,108 @@ class ShardedArrowEngine:
         be.apply_staged(dst=(0, self.ci[0]), dst_off=sh0.hoff, dst_level=0, forward=False, stage=self._stage, accumulate=True)
         self.xi[0] = self.ci[0]                                 # set_features(C_i) (:438)
 
+    # -- fused step ----------------------------------------------------------------------------------------------
+    def _setup_fused(self):
+        be, pl, fp = self.be, self.plan, self.fp
+        n_cols = fp.x_split + max(fp.recv_rows, 1)
+        self.f_mats, self.f_tables, self.f_tables_dry, self.f_head_tables, self.f_add = [None] * self.L, [None] * self.L, \
+            [None] * self.L, [None] * self.L, [None] * self.L
+        for j in range(1, self.L):
+            sh = pl.levels[j]
+            if self.mats[j] is not None:
+                self.f_mats[j] = be.fused_matrix(self.mats[j], fp.colmap[j], n_cols)
+            self.f_tables[j] = be.out_table(local=(j, 0), stage=self._stg[j - 1], which=fp.out_which[j], row=fp.out_row[j])
+            # measurement twin: every routed row lands in the local tile instead of a peer's staging slot
+            wd = np.where(fp.out_which[j] >= 0, 0, -1).astype(np.int32)
+            self.f_tables_dry[j] = be.out_table(local=(j, 0), stage=self._stg[j - 1], which=wd,
+                                                row=np.arange(sh.local_rows, dtype=np.int64))
+            if self.rank == 0:
+                self.f_head_tables[j] = be.out_table(local=(j, 0), stage=self._stg[j - 1], which=fp.head_which[j],
+                                                     row=fp.head_row[j])
+        for j in range(self.L - 1):
+            n = pl.levels[j].own_rows if j == 0 else pl.levels[j].local_rows
+            am = fp.add_map[j][pl.levels[j].hoff:pl.levels[j].hoff + n] if j == 0 else fp.add_map[j]
+            self.f_add[j] = be.map_upload(am, max(fp.stage_rows[j], 1))
+        self.f_push = be.push_plan(self._recv, fp.push_src, fp.push_bounds, fp.push_off, pl.levels[0].local_rows)
+        self.side_ctas, self.main_ctas = 2, 2
+
+    def _step_fused(self, dry: bool = False):
+        """forward push || level-0 SpMM ; deepest level first: SpMM with the [tile | receive region] operand, rows written
+        into the owners' staging tiles ; head reductions ; one final gather-add.  ``dry``: the same launches with every
+        cross-GPU effect removed (no push, no barriers, local pointer tables) -- the time this step would take if
+        communication were free; bench.py reports the difference as exposed communication."""
+        be, pl = self.be, self.plan
+        side = self.overlap
+        L = self.L
+        x = (0, self.xi[0])
+        out0 = self._other(0, self.xi[0])
+        hr = [min(self.width, pl.levels[j].rows_global) for j in range(L)]
+        if not dry:
+            be.barrier()                                        # every rank's level-0 features are in place
+            be.bcast_head(x, hr[0])
+            self._halo(0)
+        if side:
+            be.side_begin()
+        if not dry:
+            be.push(self.f_push, x, side=side)                  # forward exchange: one pass, NVLink stores
+            be.barrier(side)
+        if side:
+            be.limit_spmm(self.side_ctas)
+        for j in range(L - 1, 0, -1):
+            if self.f_mats[j] is not None and pl.levels[j].local_rows > 0:
+                be.spmm_fused(self.f_mats[j], x, self._recv, self.fp.x_split,
+                              self.f_tables_dry[j] if dry else self.f_tables[j],
+                              add=self._stg[j] if j < L - 1 else None, add_map=self.f_add[j] if j < L - 1 else None, side=side)
+            if not dry:
+                be.barrier(side)                                # partial head rows written, routed rows delivered
+                if self.rank == 0:
+                    be.reduce_rows((j, 0), hr[j], table=self.f_head_tables[j], side=side)
+                be.barrier(side)                                # ... including the reduced head rows
+        if side:
+            be.limit_spmm(self.main_ctas)
+        if self.mats[0] is not None and pl.levels[0].local_rows > 0:
+            be.spmm(self.mats[0], self.tiles[0][x[1]], self.tiles[0][out0])
+        be.limit_spmm(0)
+        if not dry:
+            be.barrier()                                        # all partial head tiles of level 0 are written
+            if self.rank == 0:
+                be.reduce_rows((0, out0), hr[0], table=None)
+        if side:
+            be.side_join()
+        # C_0[to_prev[r]] += C_1[r] (arrow_dec_mpi.py:437): the staged rows are local now
+        be.final_add((0, out0), pl.levels[0].hoff, pl.levels[0].own_rows, self._stg[0], self.f_add[0])
+        self.ci[0] = out0
+        self.xi[0] = out0                                       # set_features(C_i) (:438)
+
+    def _step_graph(self):
+        """The fused step as ONE host call: recorded once per ping-pong parity (CUDA graph, both lanes, barriers
+        included -- their epochs live in device memory) after one plain run that settles every lazy allocation."""
+        ctx = self.be.ctx
+        key = self.xi[0]
+        g = self.graphs.get(key)
+        if g is None:
+            warm = self.__dict__.setdefault("_graph_warm", set())
+            if key not in warm:
+                warm.add(key)
+                return self._step_fused()
+            xi, ci = list(self.xi), list(self.ci)
+            ctx.graph_begin()
+            try:
+                self._step_fused()                      # recorded, not executed
+            finally:
+                g = ctx.graph_end()
+            self.graphs[key] = g
+            self.xi, self.ci = xi, ci
+        ctx.graph_launch(g)
+        out0 = self._other(0, self.xi[0])
+        self.ci[0] = out0
+        self.xi[0] = out0
+
     def step(self):
+        if self.fp is not None:
+            if getattr(self, "use_graphs", False) and getattr(self.be, "ctx", None) is not None:
+                return self._step_graph()
+            return self._step_fused()
         if self.split:
             return self._step_split()
         if not self.overlap:
@@ -599,12 +920,22 @@ class CudaPeerBackend:
         arena_rows = max(-(-pos // 64), (2 << 20) // 256)       # >= 2 MiB so the driver gives it its own block
         self._arena = ctx.dense_alloc(arena_rows, 64)
         ctx.sync()
+        import os
         mine = dict(handle=self._arena.ipc_export(), arena_rows=arena_rows, offs=offs, rows=list(rows_per_level),
-                    send_off=self._send_off, send_rows=self._send_rows)
+                    send_off=self._send_off, send_rows=self._send_rows, pid=os.getpid(), ptr=self._arena.device_ptr(),
+                    device=ctx.device)
         everyone = self.comm.allgather(mine)
         self._peer, self._flags, self._flags_side, self._arenas, self._arena_base = [], [], [], [], []
         for g, info in enumerate(everyone):
-            arena = self._arena if g == self.rank else ctx.ipc_import(info["handle"], info["arena_rows"], 64)
+            if g == self.rank:
+                arena = self._arena
+            elif info["pid"] == os.getpid():
+                # ranks as threads of one process (comm.ThreadComm): same address space, no IPC mapping
+                if info["device"] != ctx.device:
+                    raise NotImplementedError("in-process ranks on different devices need peer access; use one process per GPU")
+                arena = ctx.dense_wrap(info["ptr"], info["arena_rows"], 64)
+            else:
+                arena = ctx.ipc_import(info["handle"], info["arena_rows"], 64)
             self._arenas.append(arena)
             base = arena.device_ptr()
             self._arena_base.append((base, info["send_off"]))
@@ -748,6 +1079,62 @@ class CudaPeerBackend:
     @property
     def supports_staged_exchange(self) -> bool:
         return self.plan is not None and type(self) is CudaPeerBackend
+
+    # -- fused step primitives (see FusedPlan) ----------------------------------------------------------------------
+    @property
+    def supports_fused(self) -> bool:
+        return type(self) is CudaPeerBackend
+
+    def _lane(self, side: bool):
+        self.ctx.set_lane(self.SIDE if side else 0)
+
+    def fused_matrix(self, A, colmap, n_cols):
+        return A.remap_columns(self.ctx.map_upload(colmap, n_cols), n_cols)
+
+    def out_table(self, local, stage, which, row):
+        """pointer table over [my tile ``local``] + [staging tile ``stage`` of every rank]"""
+        tiles = [self._peer[self.rank][local[0]][local[1]]] + [self._peer[g][stage[0]][stage[1]] for g in range(self.world)]
+        return self.ctx.ptrtable_upload(tiles, which, row)
+
+    def push_plan(self, recv, src_rows, bounds, offs, src_limit):
+        m = self.ctx.map_upload(src_rows, max(int(src_limit), 1))
+        dsts = []
+        for d in range(self.world):
+            cnt = int(bounds[d + 1] - bounds[d])
+            dsts.append(self._view(d, recv[0], recv[1], int(offs[d]), cnt) if cnt > 0 else None)
+        return dict(map=m, dsts=dsts, bounds=[int(b) for b in bounds], n=int(bounds[-1]))
+
+    def push(self, pp, x, side=False):
+        if pp["n"] == 0:
+            return
+        self._lane(side)
+        try:
+            self.ctx.push_rows(pp["dsts"], pp["bounds"], self._tiles[x[0]][x[1]], pp["map"])
+        finally:
+            self._lane(False)
+
+    def spmm_fused(self, A, x, recv, x_split, table, add=None, add_map=None, side=False):
+        self._lane(side)
+        try:
+            self.ctx.spmm_ex(A, self._tiles[x[0]][x[1]], X2=self._tiles[recv[0]][recv[1]], x_split=x_split, out_table=table,
+                             add=self._tiles[add[0]][add[1]] if add is not None else None, add_map=add_map)
+        finally:
+            self._lane(False)
+
+    def reduce_rows(self, tile, rows, table=None, side=False):
+        """sum of every rank's first ``rows`` rows of ``tile`` (the partial head tiles), in rank order: into my own tile,
+        or -- with a table -- wherever each row is routed"""
+        self._lane(side)
+        try:
+            srcs = [self._view(g, tile[0], tile[1], 0, rows) for g in range(self.world)]
+            self.ctx.reduce_rows(srcs, rows, dst=None if table is not None else srcs[self.rank], out_table=table)
+        finally:
+            self._lane(False)
+
+    def final_add(self, dst, dst_off, rows, stage, add_map):
+        if rows > 0:
+            self.ctx.gather_rows(self._view(self.rank, dst[0], dst[1], dst_off, rows), self._tiles[stage[0]][stage[1]],
+                                 add_map, accumulate=True)
 
     def tile_view(self, level: int, which: int, off: int, rows: int):
         return self._view(self.rank, level, which, off, rows)
@@ -921,7 +1308,7 @@ class ShardedArrowDecomposition:
     """Convenience wrapper used by bench.py at N > 1: plan + CUDA peer backend + the reference-like calls."""
 
     def __init__(self, comm, decomposition, width: int, k: int, device: int = 0, exchange: str = "p2p",
-                 overlap: bool = False, block_diagonal: bool = True):
+                 overlap: bool = False, block_diagonal: bool = True, mode: str = "auto"):
         self.comm = comm
         plan = ShardPlan(decomposition, width, comm.Get_rank(), comm.Get_size(), block_diagonal=block_diagonal)
         if exchange == "p2p":
@@ -933,7 +1320,7 @@ class ShardedArrowDecomposition:
             be = NcclBackend(comm, device, width, plan)
         else:
             raise ValueError("exchange must be 'p2p', 'p2p-direct' or 'nccl'")
-        self.engine = ShardedArrowEngine(plan, k, be, overlap=overlap)
+        self.engine = ShardedArrowEngine(plan, k, be, overlap=overlap, mode=mode)
         self.B = self
         self.matrix_index = 0
         self.decomposition_length = plan.L

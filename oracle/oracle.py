@@ -77,8 +77,9 @@ def csr_spmm_scipy(A: sparse.csr_matrix, X: np.ndarray) -> np.ndarray:
 # global view: tests/test_arrowdecomposition.py:139-156 (compute_spmm)
 # --------------------------------------------------------------------------------------
 def compute_spmm(decomposition: Sequence[Tuple[sparse.csr_matrix, np.ndarray]], X: np.ndarray) -> np.ndarray:
-    """``sum_j (B_j @ X[perm_j])[argsort(perm_j)]`` in fp32 -- the reference tests' own golden."""
-    acc = np.zeros((X.shape[0], X.shape[1]), dtype=np.float32)
+    """``sum_j (B_j @ X[perm_j])[argsort(perm_j)]`` in the precision of ``X`` (fp32 = the reference tests' own golden;
+    float64 inputs give the exact yardstick)."""
+    acc = np.zeros((X.shape[0], X.shape[1]), dtype=X.dtype)
     for B, perm in decomposition:
         inv = np.argsort(perm)
         acc += (B @ X[perm])[inv]
@@ -189,7 +190,11 @@ class ReferenceProtocolOracle:
 
     def __init__(self, decomposition: Sequence[Tuple[sparse.csr_matrix, np.ndarray]], width: int,
                  k: int, block_diagonal: bool = True, n_blocks: Optional[Sequence[int]] = None,
-                 use_c_kernel: bool = False, blockwise: bool = False):
+                 use_c_kernel: bool = False, blockwise: bool = False, dtype=np.float32):
+        """``dtype=np.float64`` turns the restatement into the exact-arithmetic yardstick the parity tests use to
+        tell rounding (any fp32 summation order, the reference's included) from a wrong result; the reference itself
+        computes in fp32 (arrow_bench.py:21)."""
+        self.dtype = np.dtype(dtype)
         self.width, self.k = width, k
         self.L = len(decomposition)
         self.n_blocks = [number_of_blocks(B, width) for B, _ in decomposition] if n_blocks is None else list(n_blocks)
@@ -198,8 +203,11 @@ class ReferenceProtocolOracle:
         self.rows = [nb * width for nb in self.n_blocks]
         self.mats = [arrow_mask(B, width, nb, block_diagonal) for (B, _), nb in zip(decomposition, self.n_blocks)]
         self.dropped_nnz = [int(sparse.csr_matrix(B).nnz - M.nnz) for (B, _), M in zip(decomposition, self.mats)]
-        self.C = [np.zeros((r, k), dtype=np.float32) for r in self.rows]       # zero_rhs (arrow_slim_mpi.py:354-394)
-        self.X = [np.zeros((r, k), dtype=np.float32) for r in self.rows]
+        if self.dtype != np.float32:
+            assert not use_c_kernel, "the C restatement of csr_matvecs is fp32 like SciPy's instantiation the reference uses"
+            self.mats = [M.astype(self.dtype) for M in self.mats]
+        self.C = [np.zeros((r, k), dtype=self.dtype) for r in self.rows]       # zero_rhs (arrow_slim_mpi.py:354-394)
+        self.X = [np.zeros((r, k), dtype=self.dtype) for r in self.rows]
         self._mm = csr_spmm_c if use_c_kernel else (lambda A, X: A @ X)
         self.blockwise = blockwise
         self.block_diagonal = block_diagonal
@@ -207,7 +215,7 @@ class ReferenceProtocolOracle:
     def set_features(self, X0: np.ndarray) -> None:
         """Level-0 tiles, in level-0 (permuted) row order; stored by reference like ``set_features``."""
         assert X0.shape == (self.rows[0], self.k)
-        self.X[0] = X0
+        self.X[0] = X0 if X0.dtype == self.dtype else X0.astype(self.dtype)
 
     # forward exchange, arrow_dec_mpi.py:507-550
     def propagate_features(self) -> None:
@@ -219,13 +227,13 @@ class ReferenceProtocolOracle:
 
     def _spmm_level(self, j: int) -> np.ndarray:
         if not self.blockwise:
-            return np.asarray(self._mm(self.mats[j], self.X[j]), dtype=np.float32)
+            return np.asarray(self._mm(self.mats[j], self.X[j]), dtype=self.dtype)
         # block algebra of arrow_slim_mpi.py:104-155: C_0 = sum_i A_0i X_i ; C_i = A_ii X_i + A_i0 X_0
         w, t = self.width, self.n_blocks[j]
         M, X = self.mats[j], self.X[j]
         out = np.zeros_like(X)
         X0 = X[:w]
-        c0 = np.zeros((w, self.k), dtype=np.float32)
+        c0 = np.zeros((w, self.k), dtype=self.dtype)
         for i in range(t):
             c0 += M[:w, i * w:(i + 1) * w] @ X[i * w:(i + 1) * w]
         out[:w] = c0

@@ -61,11 +61,80 @@ class GlooNumpyBackend:
         pass
 
     def barrier(self, side=False):
+        # remote stores issued before the barrier are visible after it: deliver the outboxes first ...
+        outbox = getattr(self, "outbox", [])
+        self.outbox = []
+        for sender in self.comm.allgather(outbox):
+            for dest, level, which, rows, data in sender:
+                if dest == self.rank:
+                    self.tiles[level][which][rows] = data
+        # ... then publish what peers may read until the next barrier
         send = getattr(self, "sendbuf", None)
         got = self.comm.allgather(([[t.copy() for t in pair] for pair in self.tiles], None if send is None else send.copy()))
         self.snap = [g[0] for g in got]
         self.snap_send = [g[1] for g in got]
         self.n_barriers += 1
+
+    # -- fused step primitives, mirroring CudaPeerBackend (remote stores = outbox entries delivered at the next barrier) --
+    supports_fused = True
+
+    def fused_matrix(self, A, colmap, n_cols):
+        A = sparse.csr_matrix(A)
+        idx = np.asarray(colmap, dtype=np.int64)[A.indices]
+        assert np.all(idx >= 0) and np.all(idx < n_cols)
+        return sparse.csr_matrix((A.data, idx, A.indptr), shape=(A.shape[0], n_cols), dtype=np.float32)
+
+    def out_table(self, local, stage, which, row):
+        return dict(local=local, stage=stage, which=np.asarray(which), row=np.asarray(row, dtype=np.int64))
+
+    def _store(self, table, values):
+        """rows of ``values`` to wherever the table routes them"""
+        which, row = table["which"], table["row"]
+        sel = np.flatnonzero(which[: values.shape[0]] == 0)
+        self.tiles[table["local"][0]][table["local"][1]][row[sel]] = values[sel]
+        for d in range(self.world):
+            sel = np.flatnonzero(which[: values.shape[0]] == 1 + d)
+            if sel.size == 0:
+                continue
+            if d == self.rank:
+                self.tiles[table["stage"][0]][table["stage"][1]][row[sel]] = values[sel]
+            else:
+                self.__dict__.setdefault("outbox", []).append((d, table["stage"][0], table["stage"][1], row[sel].copy(), values[sel].copy()))
+
+    def push_plan(self, recv, src_rows, bounds, offs, src_limit):
+        return dict(recv=recv, src=np.asarray(src_rows, dtype=np.int64), bounds=[int(b) for b in bounds], offs=[int(o) for o in offs])
+
+    def push(self, pp, x, side=False):
+        X = self.tiles[x[0]][x[1]]
+        for d in range(self.world):
+            a, b = pp["bounds"][d], pp["bounds"][d + 1]
+            if b > a:
+                assert d != self.rank
+                rows = pp["offs"][d] + np.arange(b - a, dtype=np.int64)
+                self.__dict__.setdefault("outbox", []).append((d, pp["recv"][0], pp["recv"][1], rows, X[pp["src"][a:b]].copy()))
+
+    def spmm_fused(self, A, x, recv, x_split, table, add=None, add_map=None, side=False):
+        Xc = np.concatenate([self.tiles[x[0]][x[1]][:x_split], self.tiles[recv[0]][recv[1]]])
+        prod = (A @ Xc[: A.shape[1]]).astype(np.float32)
+        if add is not None:
+            m = add_map.m[: prod.shape[0]]
+            sel = np.flatnonzero(m >= 0)
+            prod[sel] += self.tiles[add[0]][add[1]][m[sel]]
+        self._store(table, prod)
+
+    def reduce_rows(self, tile, rows, table=None, side=False):
+        total = np.zeros((rows, self.k), np.float32)
+        for g in range(self.world):
+            total += self._tile(g, tile[0], tile[1])[:rows]
+        if table is None:
+            self.tiles[tile[0]][tile[1]][:rows] = total
+        else:
+            self._store(table, total)
+
+    def final_add(self, dst, dst_off, rows, stage, add_map):
+        m = add_map.m[:rows]
+        sel = np.flatnonzero(m >= 0)
+        self.tiles[dst[0]][dst[1]][dst_off + sel] += self.tiles[stage[0]][stage[1]][m[sel]]
 
     # -- staged (two-phase) packed exchange, mirroring CudaPeerBackend.stage_rows / apply_staged -----------------
     supports_staged_exchange = True

@@ -20,17 +20,20 @@ def test_step_matches_protocol_oracle_chained(cuda_device, mode, perm_kind, k, l
     eng = ArrowEngine(dec, w, k, device=cuda_device, mode=mode)
     assert eng.mode == mode
     po = oracle.ReferenceProtocolOracle(dec, w, k)
+    po64 = oracle.ReferenceProtocolOracle(dec, w, k, dtype=np.float64)      # exact yardstick (see assert_close)
     X = synth.generate_dense_matrix(n, k, np.float32, np.random.default_rng(42))
     Xl0 = X[po.perms[0]]
     eng.set_features(Xl0)
     po.set_features(Xl0.copy())
+    po64.set_features(Xl0)
     for it in range(3):                                   # chained like tests/test_arrowmpi.py:164-166
         eng.step()
         ref = po.step()
         got = eng.result()
-        assert_close(got, ref, tol=2e-5 if it == 2 else 1e-5)
-        # re-sync the oracle's state to the device result so errors do not compound across iterations
+        assert_close(got, ref, exact=po64.step())
+        # re-sync the oracles' state to the device result so errors do not compound across iterations
         po.C[0][:] = got
+        po64.C[0][:] = got
     # against the reference tests' own golden for a fresh X
     eng.set_features(Xl0)
     eng.step()
@@ -77,11 +80,19 @@ def test_fused_styles_equal_exchange(cuda_device, levels, k):
         eng = ArrowEngine(dec, w, k, device=cuda_device, **kw)
         eng.set_features(X)
         eng.step()
+        first = eng.result()
         eng.step()                  # chained second iteration
-        res[name] = eng.result()
+        res[name] = (first, eng.result())
         eng.close()
-    assert_close(res["gather"], res["exchange"], tol=2e-5)
-    assert_close(res["scatter"], res["exchange"], tol=2e-5)
+    # exact yardstick: two float64 steps, the second one started from each engine's own first result
+    for name in ("gather", "scatter"):
+        assert_close(res[name][0], res["exchange"][0])
+        po64 = oracle.ReferenceProtocolOracle(dec, w, k, dtype=np.float64)
+        po64.set_features(X)
+        po64.step()
+        po64.C[0][:] = res["exchange"][0]
+        po64.X[0] = po64.C[0]
+        assert_close(res[name][1], res["exchange"][1], exact=po64.step())
 
 
 def test_arrow_pattern_masking(cuda_device):
@@ -178,15 +189,19 @@ def test_decomposed_graph_through_engine(cuda_device, n, w, k):
     dec = arrow_decomposition(A, w, max_number_of_levels=3, block_diagonal=True, seed=1)
     eng = ArrowEngine(dec, w, k, device=cuda_device, mode="auto")
     po = oracle.ReferenceProtocolOracle(dec, w, k)
+    po64 = oracle.ReferenceProtocolOracle(dec, w, k, dtype=np.float64)      # exact yardstick (hub rows of a BA graph)
     rng = np.random.default_rng(6)
     X = synth.generate_dense_matrix(po.rows[0], k, np.float32, rng)
     eng.set_features(X)
     po.set_features(X.copy())
+    po64.set_features(X)
     for it in range(2):
         eng.step()
         po.step()
+        po64.step()
         for j in range(po.L if eng.mode == "exchange" else 1):      # fused mode keeps only level 0's tile
-            assert_close(eng.result(j), po.C[j], tol=1e-5 if it == 0 else 3e-5)
+            assert_close(eng.result(j), po.C[j], exact=po64.C[j])
+        po64.C[0][:] = po.C[0]              # the second (chained) product is compared from the same starting point
     eng.close()
 
 

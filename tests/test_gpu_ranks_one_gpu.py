@@ -1,0 +1,163 @@
+"""The multi-rank engine on ONE GPU: ranks are threads of this process (comm.ThreadComm), every rank has its own
+library context / streams on device 0 and reads or writes its peers' tiles as plain pointers.  Every cross-rank
+mechanism of the N-GPU path runs for real -- device-side barriers over flag words, the forward push kernel, row-pointer
+epilogues into the peers' staging tiles, head reductions, the side-lane schedule, CUDA-graph replay -- only the wire is
+HBM instead of NVLink.  (One process per GPU over CUDA IPC: tests/test_gpu_multi.py, needs >= 2 GPUs.)"""
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle
+from arrow_matrix_b200 import graphio, synth
+from arrow_matrix_b200.arrow_dec_mpi import ArrowDecompositionMPI
+from arrow_matrix_b200.comm import ThreadWorld
+from arrow_matrix_b200.sharded import CudaPeerBackend, ShardPlan, ShardedArrowEngine
+
+
+def run_ranks(world, fn):
+    """fn(rank, comm) on `world` threads; the first failure aborts the collectives of the others"""
+    tw = ThreadWorld(world)
+    errors = [None] * world
+
+    def body(r):
+        comm = tw.comm(r)
+        try:
+            fn(r, comm)
+        except BaseException as e:      # noqa: BLE001
+            import traceback
+            errors[r] = traceback.format_exc()
+            comm.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not any(t.is_alive() for t in threads), "a rank is stuck"
+    real = [e for e in errors if e and "BrokenBarrierError" not in e]
+    assert not real and not any(errors), "\n".join(real or [e for e in errors if e])
+
+
+def close_rows(got, ref_level, exact_level, r0, r1, tol=1e-5):
+    """this rank's rows against the level's reference: the tolerance rule of ``assert_close`` (1e-5 of the level's largest
+    entry; beyond that only rounding that the exact float64 yardstick attributes to fp32 summation order)"""
+    if r1 <= r0:
+        return
+    scale = max(float(np.max(np.abs(ref_level))), 1e-30)
+    ref = ref_level[r0:r1]
+    err = float(np.max(np.abs(got.astype(np.float64) - ref)))
+    if err <= tol * scale:
+        return
+    ex = exact_level[r0:r1]
+    e_got = float(np.max(np.abs(got.astype(np.float64) - ex)))
+    e_ref = float(np.max(np.abs(ref.astype(np.float64) - ex)))
+    assert e_got <= max(tol * scale, 2.0 * e_ref), (err / scale, e_got / scale, e_ref / scale)
+
+
+CASES = {"L2k128": (128, 9, 128, 2, True, False), "L2k16": (64, 12, 16, 2, True, False), "L3k16": (64, 11, 16, 3, True, False),
+         "L4k8": (32, 16, 8, 4, True, False), "L3stale_k6": (32, 6, 6, 3, False, False), "banded_k8": (32, 9, 8, 2, True, True),
+         "L2k5": (32, 7, 5, 2, True, False)}
+
+
+@pytest.mark.parametrize("schedule", ["fused", "fused+side", "fused+side+graph", "exchange", "exchange+overlap", "exchange+overlap2",
+                                      "p2p-direct"])
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("world", [2, 3])
+def test_rank_threads_match_protocol_oracle(cuda_device, world, case, schedule):
+    w, t0, k, levels, nested, banded = CASES[case]
+    if world == 3 and case in ("L2k128", "L4k8") and "graph" not in schedule and schedule != "fused":
+        pytest.skip("covered at world 2")
+    dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600,
+                                    band_nnz=4 if banded else 0, shrink=1 if banded else 2)
+    po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=not banded)
+    po64 = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=not banded, dtype=np.float64)
+    rng = np.random.default_rng(2)
+    Xs = [synth.generate_dense_matrix(t0 * w, k, np.float32, rng) for _ in range(3)]
+    refs, exacts = [], []
+    for it, X in enumerate(Xs):
+        if it != 1:                                         # iteration 1 is chained (X := A X)
+            po.set_features(X.copy())
+            po64.set_features(X)
+        po.step()
+        po64.step()
+        refs.append([c.copy() for c in po.C])
+        exacts.append([c.copy() for c in po64.C])
+    fused = schedule.startswith("fused")
+
+    def rank_body(rank, comm):
+        plan = ShardPlan(dec, w, rank, world, block_diagonal=not banded)
+        be = CudaPeerBackend(comm, cuda_device, w, plan=None if schedule == "p2p-direct" else plan)
+        be.layout_plan = plan
+        overlap = 2 if schedule.endswith("overlap2") else ("side" in schedule or "overlap" in schedule)
+        eng = ShardedArrowEngine(plan, k, be, overlap=overlap, mode="auto" if fused else "exchange")
+        if fused and nested:
+            assert eng.fp is not None, eng.mode
+        if "graph" in schedule and eng.fp is not None:
+            eng.use_graphs = True
+        sh0 = plan.levels[0]
+        for it, X in enumerate(Xs):
+            if it != 1:
+                eng.set_features(X[sh0.r0:sh0.r1])
+            eng.step()
+            for j in range(1 if eng.fp is not None else plan.L):
+                sh = plan.levels[j]
+                close_rows(eng.result(j), refs[it][j], exacts[it][j], sh.r0, sh.r1)
+        eng.sync()
+        comm.Barrier()
+        eng.close()
+
+    run_ranks(world, rank_body)
+
+
+def test_public_classes_on_rank_threads_from_files(cuda_device, tmp_path):
+    """files -> load_decomposition_new -> initialize -> load_sparse_matrix_from_blocks -> step on 2 ranks (every rank slices
+    its own rows out of the memory-mapped level files), fused step, host-staged streaming iteration included"""
+    w, t0, k = 64, 10, 32
+    dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=12, hub_rows=1, hub_nnz=300)
+    base = str(tmp_path / "g")
+    graphio.save_decomposition_new(dec, base, w, block_diagonal=True)
+    po = oracle.ReferenceProtocolOracle(dec, w, k)
+    rng = np.random.default_rng(3)
+    Xs = [synth.generate_dense_matrix(t0 * w, k, np.float32, rng) for _ in range(4)]
+    refs = []
+    for X in Xs:
+        po.set_features(X.copy())
+        refs.append(po.step().copy())
+
+    def rank_body(rank, comm):
+        from arrow_matrix_b200 import _lib
+        blocks, n_blocks, to_prev, to_next = ArrowDecompositionMPI.load_decomposition_new(comm, base, w, True, slim=True)
+        arrow = ArrowDecompositionMPI.initialize(comm, n_blocks, to_prev, to_next, w, k, 'gpu', True, True)
+        arrow.B.load_sparse_matrix_from_blocks(blocks)
+        arrow.B.zero_rhs(w, k)
+        eng = arrow._engine
+        assert eng.fp is not None and eng.mode.startswith("fused")
+        sh0 = eng.plan.levels[0]
+        scale = max(float(np.max(np.abs(r))) for r in refs)
+        for X, ref in zip(Xs, refs):
+            arrow.B.set_features(X[sh0.r0:sh0.r1])
+            arrow.step()
+            got = arrow.B.result_tile()
+            assert float(np.max(np.abs(got - ref[sh0.r0:sh0.r1]))) <= 1e-5 * scale
+        # streaming iteration: pinned host buffers in rotation, results identical to the blocking calls
+        n = sh0.own_rows
+        hx = [_lib.PinnedArray((n, k)) for _ in range(2)]
+        hc = [_lib.PinnedArray((n, k)) for _ in range(2)]
+        outs = []
+        for i, X in enumerate(Xs):
+            if i >= 2:
+                arrow.synchronize()
+                outs.append(hc[i % 2].array.copy())
+            hx[i % 2].array[:] = X[sh0.r0:sh0.r1]
+            arrow.step_stream(hx[i % 2].array, hc[i % 2].array)
+        arrow.synchronize()
+        outs += [hc[(len(Xs) - 2) % 2].array.copy(), hc[(len(Xs) - 1) % 2].array.copy()]
+        for got, ref in zip(outs, refs):
+            assert float(np.max(np.abs(got - ref[sh0.r0:sh0.r1]))) <= 1e-5 * scale
+        comm.Barrier()
+        eng.close()
+
+    run_ranks(2, rank_body)

@@ -82,7 +82,9 @@ def test_bench_spmm_driver_and_cli(cuda_device, tmp_path, monkeypatch):
     for _ in range(3):
         X = 2 * rng.random((4000, 64), dtype=np.float32) - 1        # the driver's last features (rng 42 + rank)
     got = arrow.B.result_tile()
-    assert_close(oracle.to_original_order(got, dec[0][1], 4000), oracle.compute_spmm(dec, X[np.argsort(dec[0][1])]), tol=2e-5)
+    Xo = X[np.argsort(dec[0][1])]
+    exact = oracle.compute_spmm([(B.astype(np.float64), p) for B, p in dec], Xo.astype(np.float64)).astype(np.float64)
+    assert_close(oracle.to_original_order(got, dec[0][1], 4000), oracle.compute_spmm(dec, Xo), exact=exact)
     with pytest.raises(NotImplementedError):
         arrow_bench.bench_spmm(None, 100, 2, 1, True, 'cpu', p_per_side=2, verbose=False)
     from arrow_matrix_b200 import cli
@@ -99,9 +101,12 @@ def test_bench_spmm_reference_route_ba_graph(cuda_device, tmp_path, monkeypatch)
     dec = graphio.load_decomposition_new("tmp/test_ba_6_4", 64, True)
     assert 1 <= len(dec) <= 3 and arrow.decomposition_length == len(dec)
     po = oracle.ReferenceProtocolOracle(dec, 64, 8)
+    po64 = oracle.ReferenceProtocolOracle(dec, 64, 8, dtype=np.float64)
     rng = np.random.default_rng(42)
     for _ in range(2):                                   # the driver sets fresh features before every iteration
         X = 2 * rng.random((po.rows[0], 8), dtype=np.float32) - 1
         po.set_features(X.copy())
+        po64.set_features(X)
         ref = po.step()
-    assert_close(arrow.B.result_tile(), ref, tol=2e-5)
+        exact = po64.step()
+    assert_close(arrow.B.result_tile(), ref, exact=exact)

@@ -76,9 +76,19 @@ def _run_case(rank, world, case, overlap):
     if case == "banded":
         bd = False
     plan = ShardPlan(dec, w, rank, world, block_diagonal=bd)
-    eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=overlap)
-    assert eng.overlap == bool(overlap)
-    assert eng.split == (overlap == 2 and plan.L == 2 and world > 1)
+    fused = isinstance(overlap, str)            # "fused" / "fused-side": the fused step (serial / side-lane schedule)
+    if fused:
+        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=(overlap == "fused-side"), mode="auto")
+        # rows behind the sentinel only force the literal protocol when some non-zero READS one of them (then the
+        # engine must have fallen back on its own); either way the numbers below have to match the oracle
+        if case == "L3stale":
+            assert not eng.fused_ok and eng.fp is None, (case, eng.mode)
+        elif not case.endswith(("nonnested_k3", "stale_k7")):
+            assert eng.fused_ok and eng.fp is not None, (case, eng.mode)
+    else:
+        eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=overlap, mode="exchange")
+        assert eng.overlap == bool(overlap)
+        assert eng.split == (overlap == 2 and plan.L == 2 and world > 1)
     po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=bd)
     assert eng.total_nnz == sum(M.nnz for M in po.mats)
     sh0 = plan.levels[0]
@@ -88,11 +98,24 @@ def _run_case(rank, world, case, overlap):
             po.set_features(X.copy())
         eng.step()
         po.step()
-        for j in range(plan.L):
+        for j in range(plan.L if eng.fp is None else 1):        # the fused step materialises level 0 only
             sh = plan.levels[j]
             got = eng.result(j)
             assert got.shape == (sh.own_rows, k)
             assert np.allclose(got, po.C[j][sh.r0:sh.r1], rtol=1e-5, atol=1e-5), (case, rank, it, j)
+    if eng.fp is not None:
+        with pytest.raises(RuntimeError):
+            eng.result(1)
+        # the phase-by-phase surface falls back to the literal protocol and keeps producing the same numbers
+        eng.ensure_level_tiles()
+        assert eng.fp is None
+        eng.step()
+        po.step()
+        for j in range(plan.L):
+            sh = plan.levels[j]
+            ref = po.C[j][sh.r0:sh.r1]
+            err = float(np.max(np.abs(eng.result(j) - ref))) / max(float(np.max(np.abs(po.C[j]))), 1e-30) if ref.size else 0.0
+            assert err <= 1e-5, (case, rank, "after fallback", j, err)      # third chained product: max-norm relative
     assert comm.allreduce_lor(False) is False
 
 
@@ -106,7 +129,17 @@ CASES = [(w, c, False) for w in (2, 3) for c in ["L2", "L3", "L3stale", "small",
          (3, "golden:wide_L3_banded_stale_k7", True), (4, "golden:slim_L4_nested_k6", False),
          # overlap=2: split level-0 product, staged backward exchange (two levels; else falls back)
          (2, "L2", 2), (3, "L2", 2), (4, "small", 2), (3, "golden:slim_L2_random_k4", 2),
-         (3, "golden:slim_L2_short_file_k4", 2), (3, "L3", 2)]
+         (3, "golden:slim_L2_short_file_k4", 2), (3, "L3", 2),
+         # the fused step (push exchange folded into the products), serial and side-lane schedules; stale-row
+         # decompositions must fall back to the literal protocol on their own
+         (2, "L2", "fused"), (2, "L3", "fused-side"), (2, "small", "fused"), (2, "banded", "fused"), (2, "L3stale", "fused"),
+         (2, "golden:slim_L2_hubs_k16", "fused-side"), (2, "golden:slim_L4_nested_k6", "fused"),
+         (2, "golden:wide_L2_banded_k4", "fused"), (2, "decomposed", "fused-side"),
+         (3, "L2", "fused-side"), (3, "L3", "fused"), (3, "banded", "fused-side"), (3, "golden:slim_L2_random_k4", "fused"),
+         (3, "golden:slim_L3_nonnested_k3", "fused"), (3, "golden:slim_L2_julia_quirks_k4", "fused"),
+         (3, "decomposed-1000", "fused"), (3, "golden:wide_L3_banded_stale_k7", "fused-side"),
+         (4, "L2", "fused"), (4, "small", "fused-side"), (4, "banded", "fused"), (4, "golden:slim_L4_nested_k6", "fused-side"),
+         (4, "golden:wide_L2_random_k5", "fused")]
 
 
 @pytest.mark.parametrize("world", [2, 3, 4])
