@@ -140,6 +140,8 @@ struct arrow_ctx {
     int *tile_ticket = nullptr;       // device: per lane {next tile, finished CTAs} of the dynamic tile scheduler
     std::vector<PtrTable> ptrtabs;
     std::vector<cudaGraphExec_t> graphs;
+    std::vector<int64_t> graph_kernels;           // kernels recorded in each graph (arrow_launch_count stays truthful under replay)
+    int64_t capture_launches0 = 0;
     bool capturing = false;
     cudaStream_t lanes[ARROW_N_LANES] = {};   // lane 0 = main stream
     cudaEvent_t lane_events[ARROW_N_LANES] = {};
@@ -2723,6 +2725,7 @@ int arrow_graph_begin(arrow_ctx *ctx) {
     if (ctx->capturing) return fail(ctx, ARROW_ERR_ARG, "a capture is already in progress");
     CUDA_TRY(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
+    ctx->capture_launches0 = ctx->launches;
     ctx->cur_lane = 0;
     return ARROW_OK;
 }
@@ -2731,6 +2734,8 @@ int arrow_graph_end(arrow_ctx *ctx, int *graph_out) {
     CHECK_CTX(ctx);
     if (!ctx->capturing) return fail(ctx, ARROW_ERR_ARG, "no capture in progress");
     ctx->capturing = false;
+    const int64_t recorded = ctx->launches - ctx->capture_launches0;
+    ctx->launches = ctx->capture_launches0;                  // recorded, not executed
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
     if (e != cudaSuccess || !g) {
@@ -2748,8 +2753,9 @@ int arrow_graph_end(arrow_ctx *ctx, int *graph_out) {
     int h = -1;
     for (size_t i = 0; i < ctx->graphs.size(); ++i)
         if (!ctx->graphs[i]) { h = (int)i; break; }
-    if (h < 0) { ctx->graphs.push_back(nullptr); h = (int)ctx->graphs.size() - 1; }
+    if (h < 0) { ctx->graphs.push_back(nullptr); ctx->graph_kernels.push_back(0); h = (int)ctx->graphs.size() - 1; }
     ctx->graphs[h] = ex;
+    ctx->graph_kernels[h] = recorded;
     *graph_out = h;
     return ARROW_OK;
 }
@@ -2760,7 +2766,7 @@ int arrow_graph_launch(arrow_ctx *ctx, int graph) {
     if (graph < 0 || graph >= (int)ctx->graphs.size() || !ctx->graphs[graph]) return fail(ctx, ARROW_ERR_HANDLE, "bad graph handle %d", graph);
     if (ctx->capturing) return fail(ctx, ARROW_ERR_ARG, "cannot launch a graph while capturing");
     CUDA_TRY(ctx, cudaGraphLaunch(ctx->graphs[graph], ctx->stream));
-    ctx->launches += 1;
+    ctx->launches += ctx->graph_kernels[graph];
     return ARROW_OK;
 }
 
@@ -2792,6 +2798,16 @@ static int numa_node_of_device(int device) {
 }
 
 int arrow_bind_thread_to_device_numa(int device, int *node_out, int *n_cpus_out) {
+    if (device < 0) {                                    // undo: every CPU, default memory policy
+        cpu_set_t all;
+        CPU_ZERO(&all);
+        for (int c = 0; c < CPU_SETSIZE; ++c) CPU_SET(c, &all);
+        sched_setaffinity(0, sizeof all, &all);
+        syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+        if (node_out) *node_out = -1;
+        if (n_cpus_out) *n_cpus_out = 0;
+        return ARROW_OK;
+    }
     int node = numa_node_of_device(device);
     if (node_out) *node_out = node;
     if (n_cpus_out) *n_cpus_out = 0;

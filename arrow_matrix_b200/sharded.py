@@ -586,8 +586,11 @@ class ShardedArrowEngine:
 
     def close(self):
         if getattr(self.be, "ctx", None) is not None:
-            self.be.sync()
-            self.be.ctx.close()
+            if hasattr(self.be, "close"):
+                self.be.close()
+            else:
+                self.be.sync()
+                self.be.ctx.close()
 
     # -- the iteration -----------------------------------------------------------------------------------------
     def propagate_features(self):
@@ -888,6 +891,30 @@ class CudaPeerBackend:
         self._peer = None         # [rank][level][which] -> Dense (imported or own)
         self._flags = None
         self._ident = {}
+
+    def close(self):
+        """Collective.  An exported arena must outlive every peer's mapping of it (CUDA IPC): all ranks finish their
+        work and drop their mappings, meet, and only then free their own memory."""
+        if self.ctx is None:
+            return
+        ctx = self.ctx
+        try:
+            for lane in (1, 2, 3):
+                ctx.lane_sync(lane)
+            ctx.sync()
+        except Exception:       # noqa: BLE001  (a poisoned context still has to release its mappings)
+            pass
+        for g, arena in enumerate(getattr(self, "_arenas", []) or []):
+            if g != self.rank:
+                try:
+                    arena.free()
+                except Exception:       # noqa: BLE001
+                    pass
+        try:
+            self.comm.Barrier()
+        finally:
+            ctx.close()
+            self.ctx = None
 
     def csr_upload(self, n_rows, n_cols, indptr, indices, data):
         return self.ctx.csr_upload(n_rows, n_cols, indptr, indices, data)

@@ -152,7 +152,7 @@ int  arrow_host_alloc(size_t bytes, void **ptr);
 int  arrow_host_free(void *ptr);
 /* Pinned staging memory placed on the NUMA node of `device` (mmap + mbind + first touch + cudaHostRegister); freed with
  * arrow_host_free.  arrow_bind_thread_to_device_numa pins the calling thread to that node's CPUs (node_out = -1 when
- * the topology is unknown: nothing is changed). */
+ * the topology is unknown: nothing is changed); device < 0 undoes it (every CPU, default memory policy). */
 int  arrow_host_alloc_numa(size_t bytes, int device, void **ptr);
 int  arrow_bind_thread_to_device_numa(int device, int *node_out, int *n_cpus_out);
 

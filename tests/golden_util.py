@@ -11,12 +11,8 @@ CASES = sorted(os.path.basename(p)[:-4] for pattern in ("slim_*.npz", "wide_*.np
                for p in glob.glob(os.path.join(GOLDEN_DIR, pattern)))
 
 
-# the cases the CUDA engine has been run against on a B200 (tests/test_gpu_engine.py); fixtures added later are consumed
-# by the CPU tests (oracle, loader, sharded engine over gloo) until a hardware run has covered them
-GPU_CASES = ["slim_L2_hubs_k16", "slim_L2_julia_quirks_k4", "slim_L2_random_k4", "slim_L2_short_file_k4",
-             "slim_L3_nonnested_k3", "wide_L2_banded_k4", "wide_L2_random_k5"]
-if os.environ.get("ARROW_TEST_ALL_GOLDEN_GPU") == "1":
-    GPU_CASES = list(CASES)
+# every reference-generated fixture runs through the CUDA engine (tests/test_gpu_engine.py)
+GPU_CASES = list(CASES)
 
 
 class GoldenCase:
