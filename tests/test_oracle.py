@@ -228,4 +228,32 @@ def test_bench_full_size_property_matches_the_protocol(levels, nested, tmp_path)
         assert bench.verify_ones_step(FakeEngine(1.001), dec, w, 0, Host(), Host(), SelfComm())["ok"] is False
     else:
         assert "skipped" in v
-    assert "error" in bench.verify_ones_step(None, dec, w, 0, Host(), Host(), SelfComm()) or not state_free
+
+    # the property the bench line carries since round 2: rank-1 random features.  Unlike all-ones features it must notice
+    # a wrong exchange map / column index (every row of X differs)
+    u, vv = bench.rank1_vectors(po.rows[0], k)
+    y, sf = bench.expected_step_on_vector(dec, w, u)
+    assert sf == state_free
+    if state_free:
+        po = oracle.ReferenceProtocolOracle(dec, w, k, dtype=np.float64)
+        po.set_features(u[:, None] * vv[None, :])
+        assert np.allclose(po.step(), y[:, None] * vv[None, :], rtol=1e-12, atol=1e-12)
+    po = oracle.ReferenceProtocolOracle(dec, w, k)
+    v = bench.verify_rank1_step(FakeEngine(), dec, w, 0, Host(), Host(), SelfComm())
+    if state_free:
+        assert v["ok"] and v["max_rel_err"] <= 1e-5 and v["rows"] == po.rows[0], v
+        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        assert bench.verify_rank1_step(FakeEngine(1.001), dec, w, 0, Host(), Host(), SelfComm())["ok"] is False
+
+        class WrongMap(FakeEngine):                      # an engine that routes two feature rows to the wrong place
+            def set_features(self, X):
+                X = X.copy()
+                X[[1, w + 2]] = X[[w + 2, 1]]
+                po.set_features(X)
+        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        assert bench.verify_rank1_step(WrongMap(), dec, w, 0, Host(), Host(), SelfComm())["ok"] is False
+        po = oracle.ReferenceProtocolOracle(dec, w, k)
+        assert bench.verify_ones_step(WrongMap(), dec, w, 0, Host(), Host(), SelfComm())["ok"] is True      # blind: why it was replaced
+        assert "error" in bench.verify_rank1_step(None, dec, w, 0, Host(), Host(), SelfComm())
+    else:
+        assert "skipped" in v
