@@ -51,34 +51,63 @@ def _forest_preorder(n: int, rows: np.ndarray, cols: np.ndarray, rng: np.random.
     order = order[1:]                                        # drop the super-root
     parent = pred[:n].astype(np.int64)
     parent[parent == sup] = -1
+    # depth of every vertex by pointer doubling, then the vertices grouped by depth (everything below is one vectorised
+    # pass per tree level instead of a Python loop per vertex / per component: a pruned power-law graph leaves 1e5-1e6
+    # tiny components per level)
+    depth = (parent >= 0).astype(np.int64)
+    anc = parent.copy()
+    while True:
+        live = anc >= 0
+        up = np.where(live, anc, 0)
+        more = live & (parent[up] >= 0)
+        if not more.any():
+            break
+        depth = np.where(live, depth + depth[up], depth)
+        anc = np.where(live, anc[up], -1)
+        # after a jump ``anc`` may land on a root: its depth contribution is already counted
+    by_depth = np.argsort(depth, kind="stable")
+    d_sorted = depth[by_depth]
+    max_d = int(d_sorted[-1]) if n else 0
+    cut = np.searchsorted(d_sorted, np.arange(max_d + 2), side="left")
     size = np.ones(n, dtype=np.int64)
-    for v in order[::-1]:                                    # reverse BFS order: children before parents
-        p = parent[v]
-        if p >= 0:
-            size[p] += size[v]
-    # children of every vertex, largest subtree first (they are pushed in that order, popped smallest first)
+    for d in range(max_d, 0, -1):                            # children before parents
+        vs = by_depth[cut[d]:cut[d + 1]]
+        np.add.at(size, parent[vs], size[vs])
+    # children of every vertex sorted largest subtree first; the reference pushes them in that order and pops the
+    # smallest first, so a vertex is visited after the siblings that FOLLOW it in this list: its pre-order offset below
+    # its parent is 1 + the sizes of those siblings
     has_p = parent >= 0
     kids = np.flatnonzero(has_p)
     key = np.lexsort((-size[kids], parent[kids]))
     kids = kids[key]
-    starts = np.searchsorted(parent[kids], np.arange(n), side="left")
-    ends = np.searchsorted(parent[kids], np.arange(n), side="right")
+    off = np.zeros(n, dtype=np.int64)
+    if kids.size:
+        ksz = size[kids]
+        csum = np.cumsum(ksz)
+        grp_first = np.flatnonzero(np.concatenate([[True], parent[kids][1:] != parent[kids][:-1]]))
+        grp_id = np.cumsum(np.concatenate([[True], parent[kids][1:] != parent[kids][:-1]])) - 1
+        grp_last = np.concatenate([grp_first[1:], [kids.size]]) - 1
+        total_to_end = csum[grp_last][grp_id]                # cumulative size up to the end of the kid's sibling group
+        off[kids] = 1 + (total_to_end - csum)                # sizes of the siblings listed after it
+    # components in label order, like igraph's clustering; small ones keep ascending vertex ids, large ones are laid out
+    # in the pre-order computed from the offsets, level by level
+    comp_order = np.argsort(label, kind="stable")            # members of component c: ascending ids, contiguous
+    comp_start = np.concatenate([[0], np.cumsum(comp_size)]).astype(np.int64)
     out = np.empty(n, dtype=np.int64)
-    pos = 0
-    for c in range(n_comp):                                  # components in label order, like igraph's clustering
-        root = int(first[c])
-        if comp_size[c] <= base_size:
-            members = np.flatnonzero(label == c)
-            out[pos:pos + members.size] = members
-            pos += members.size
-            continue
-        stack = [root]
-        while stack:
-            v = stack.pop()
-            out[pos] = v
-            pos += 1
-            stack.extend(kids[starts[v]:ends[v]].tolist())
-    assert pos == n
+    small = comp_size[label] <= base_size
+    pre = np.full(n, -1, dtype=np.int64)
+    # position of a small component's member = start of the component + its rank inside the component
+    rank_in_comp = np.empty(n, dtype=np.int64)
+    rank_in_comp[comp_order] = np.arange(n, dtype=np.int64) - comp_start[label[comp_order]]
+    pre[small] = comp_start[label[small]] + rank_in_comp[small]
+    roots = np.flatnonzero(~has_p & ~small)
+    pre[roots] = comp_start[label[roots]]
+    for d in range(1, max_d + 1):                            # parents before children
+        vs = by_depth[cut[d]:cut[d + 1]]
+        vs = vs[~small[vs]]
+        pre[vs] = pre[parent[vs]] + off[vs]
+    assert pre.min() >= 0
+    out[pre] = np.arange(n, dtype=np.int64)
     return out
 
 
@@ -89,19 +118,32 @@ def _bfs_order(n: int, rows: np.ndarray, cols: np.ndarray, base_size: int = 2) -
     G = sparse.coo_matrix((np.ones(rows.size), (rows, cols)), shape=(n, n)).tocsr()
     G = G.maximum(G.T)
     n_comp, label = csgraph.connected_components(G, directed=False)
-    out = []
-    seen_comp = np.zeros(n_comp, dtype=bool)
-    for v in range(n):
-        c = label[v]
-        if seen_comp[c]:
-            continue
-        seen_comp[c] = True
-        members = np.flatnonzero(label == c)
-        if members.size <= base_size:
-            out.append(members)
-        else:
-            out.append(csgraph.breadth_first_order(G, int(members[0]), directed=False, return_predecessors=False))
-    return np.concatenate(out).astype(np.int64)
+    # components in the order of their first vertex; members grouped once (ascending ids inside a component)
+    comp_size = np.bincount(label, minlength=n_comp)
+    comp_order = np.argsort(label, kind="stable")
+    comp_start = np.concatenate([[0], np.cumsum(comp_size)]).astype(np.int64)
+    first = comp_order[comp_start[:-1]]
+    # ONE breadth-first search from a virtual super-root attached to the first vertex of every large component: the
+    # queue interleaves the components but keeps each component's own FIFO order, so the sub-sequence of a component is
+    # exactly its stand-alone BFS order (a search per component re-validates the whole graph every time: minutes at 1e5
+    # components)
+    big = np.flatnonzero(comp_size > base_size)
+    key = np.empty(n, dtype=np.int64)                        # position inside the component's block of the output
+    rank_in_comp = np.empty(n, dtype=np.int64)
+    rank_in_comp[comp_order] = np.arange(n, dtype=np.int64) - comp_start[label[comp_order]]
+    key[:] = rank_in_comp                                    # small components: ascending vertex ids
+    if big.size:
+        sup = n
+        roots = np.sort(first[big])
+        aug = sparse.vstack([sparse.hstack([G, sparse.csr_matrix((n, 1))]),
+                             sparse.csr_matrix((np.ones(roots.size), (np.zeros(roots.size, dtype=np.int64), roots)),
+                                               shape=(1, n + 1))]).tocsr()
+        aug = aug.maximum(aug.T)
+        order = csgraph.breadth_first_order(aug, sup, directed=False, return_predecessors=False)[1:]
+        key[order] = np.arange(order.size, dtype=np.int64)   # global BFS position: monotone inside every component
+    comp_rank = np.empty(n_comp, dtype=np.int64)             # components in the order of their first vertex
+    comp_rank[np.argsort(first, kind="stable")] = np.arange(n_comp, dtype=np.int64)
+    return np.lexsort((key, comp_rank[label])).astype(np.int64)
 
 
 def _linear_order(A: sparse.csr_matrix, arrow_width: int, deterministic: bool, rng: np.random.Generator) -> np.ndarray:

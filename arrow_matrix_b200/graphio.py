@@ -168,7 +168,10 @@ def load_decomposition_new(filename: str, width: int = None, block_diagonal: boo
             if os.path.exists(p):
                 data = np.lib.format.open_memmap(p, mode="r") if mem_map else np.load(p)
             else:
-                data = None if mem_map else np.ones(indices.size, dtype=np.float32)
+                # value-less level files (Julia converter): the reference hands out ones in both modes (graphio.py:292-298);
+                # the memory-mapped route gets them as a zero-stride broadcast view: no nnz-sized allocation, and every
+                # consumer of the documented (data, indices, indptr) triplet can slice it
+                data = np.broadcast_to(np.float32(1), (indices.size,)) if mem_map else np.ones(indices.size, dtype=np.float32)
             if mem_map:
                 B = (data, indices, indptr)
             else:

@@ -546,6 +546,7 @@ class ShardedArrowEngine:
         return self.plan.levels[level].own_rows
 
     def zero_rhs(self):
+        self.be.barrier()               # no peer may still be reading (direct pulls) or writing (pushes) these tiles
         for pair in self.tiles:
             for t in pair:
                 self.be.fill(t, 0.0)
