@@ -145,3 +145,42 @@ def block_partition(n_blocks: int, parts: int) -> np.ndarray:
     rank 0) always belongs to rank 0, and with fewer blocks than GPUs the trailing ranks own nothing."""
     g = np.arange(parts + 1, dtype=np.int64)
     return (g * n_blocks + parts - 1) // parts
+
+
+def locality_partition(to_prev: np.ndarray, n_blocks: int, width: int, prev_bounds_rows: np.ndarray, parts: int,
+                       min_local: float = 0.5, max_skew: float = 4.0) -> Optional[np.ndarray]:
+    """Permutation-aware split of a level's block-rows (bounds array like ``block_partition``), or ``None``.
+
+    ``to_prev[r]`` is the row of the level above that row ``r`` exchanges with; ``prev_bounds_rows`` says which GPU owns
+    which rows there.  Every block-row votes for the GPU that owns most of its partners; if the votes are monotone
+    (so the shards stay contiguous ranges), at least ``min_local`` of all routed rows then stay on their GPU and no shard
+    exceeds ``max_skew`` times the even share, the level is cut where its rows map -- the exchange turns into local
+    loads.  A uniformly random permutation fails the locality test and keeps the even split.  (The reference fixes
+    one rank per block-row and always pays the all-to-all, arrow_dec_mpi.py:134-160.)"""
+    rows = n_blocks * width
+    if n_blocks < 1 or parts < 2:
+        return None
+    tp = np.asarray(to_prev[:rows])
+    valid = tp < int(prev_bounds_rows[-1])
+    owner = np.searchsorted(prev_bounds_rows, np.where(valid, tp, 0), side="right") - 1
+    blk = np.arange(rows, dtype=np.int64) // width
+    votes = np.zeros((n_blocks, parts), dtype=np.int64)
+    np.add.at(votes, (blk[valid], owner[valid]), 1)
+    routed = votes.sum(axis=1)
+    choice = np.argmax(votes, axis=1)
+    choice[0] = 0                                           # block-row 0 (the arrow head) lives on GPU 0
+    choice = np.where(routed > 0, choice, -1)
+    # blocks without any routed row follow their predecessor
+    for b in range(1, n_blocks):
+        if choice[b] < 0:
+            choice[b] = choice[b - 1]
+    if np.any(np.diff(choice) < 0):
+        return None
+    local = int(votes[np.arange(n_blocks), choice].sum())
+    if routed.sum() == 0 or local < min_local * routed.sum():
+        return None
+    bounds = np.searchsorted(choice, np.arange(parts + 1), side="left").astype(np.int64)
+    bounds[-1] = n_blocks
+    if np.max(np.diff(bounds)) > max_skew * max(n_blocks / parts, 1.0):
+        return None
+    return bounds

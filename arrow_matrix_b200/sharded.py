@@ -40,8 +40,11 @@ class LevelShard:
 
 class ShardPlan:
     def __init__(self, decomposition: Sequence[Tuple[decomp.Level, np.ndarray]], width: int, rank: int, world: int,
-                 block_diagonal: bool = True, n_blocks: Optional[Sequence[int]] = None):
+                 block_diagonal: bool = True, n_blocks: Optional[Sequence[int]] = None, partition: str = "locality"):
+        """``partition``: 'even' = every level cut into equal contiguous shards; 'locality' (default) = a level whose
+        permutation keeps most rows near their partners is cut where its rows map (``decomp.locality_partition``)."""
         self.block_diagonal = bool(block_diagonal)
+        self.partition_used = []
         self.width, self.rank, self.world = int(width), int(rank), int(world)
         self.L = len(decomposition)
         self.n_blocks = [decomp.number_of_blocks(B, width) for B, _ in decomposition] if n_blocks is None \
@@ -54,7 +57,13 @@ class ShardPlan:
             nb = self.n_blocks[j]
             sh = LevelShard()
             sh.level, sh.n_blocks, sh.rows_global = j, nb, nb * w
-            sh.bounds = decomp.block_partition(nb, world) * w                 # global row bounds per rank
+            bounds_blocks = None
+            if partition == "locality" and j > 0 and self.block_diagonal:
+                bounds_blocks = decomp.locality_partition(self.to_prev[j], nb, w, self.levels[j - 1].bounds, world)
+            self.partition_used.append("even" if bounds_blocks is None else "locality")
+            if bounds_blocks is None:
+                bounds_blocks = decomp.block_partition(nb, world)
+            sh.bounds = bounds_blocks * w                                     # global row bounds per rank
             sh.r0, sh.r1 = int(sh.bounds[rank]), int(sh.bounds[rank + 1])
             sh.own_rows = sh.r1 - sh.r0
             self._layout(sh, rank)

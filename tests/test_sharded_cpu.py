@@ -66,7 +66,7 @@ def _run_case(rank, world, case, overlap):
     else:
         w, t0, k, levels, kind, nested = {"L2": (16, 7, 8, 2, "random", True), "L3": (8, 9, 5, 3, "random", True),
                                           "L3stale": (8, 6, 4, 3, "random", False), "small": (8, 2, 4, 2, "random", True),
-                                          "banded": (8, 9, 4, 2, "random", True)}[case]
+                                          "banded": (8, 9, 4, 2, "random", True), "local16": (8, 16, 4, 2, "local", True)}[case]
         dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind=kind, seed=77, nested=nested, hub_rows=2, hub_nnz=40,
                                         band_nnz=3 if case == "banded" else 0, shrink=1 if case == "banded" else 2)
         rng = np.random.default_rng(5)
@@ -76,6 +76,13 @@ def _run_case(rank, world, case, overlap):
     if case == "banded":
         bd = False
     plan = ShardPlan(dec, w, rank, world, block_diagonal=bd)
+    if case == "local16":
+        # shard-local permutation: level 1 is cut where its rows map, so (apart from the head rows) nothing is exchanged
+        assert plan.partition_used == ["even", "locality"], plan.partition_used
+        from arrow_matrix_b200.sharded import FusedPlan
+        assert FusedPlan(plan).recv_rows <= w
+        even = comm.allgather(FusedPlan(ShardPlan(dec, w, rank, world, block_diagonal=bd, partition="even")).recv_rows)
+        assert max(even) > w, even                          # the even split would have sent whole shards across
     fused = isinstance(overlap, str)            # "fused" / "fused-side": the fused step (serial / side-lane schedule)
     if fused:
         eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=(overlap == "fused-side"), mode="auto")
@@ -139,7 +146,8 @@ CASES = [(w, c, False) for w in (2, 3) for c in ["L2", "L3", "L3stale", "small",
          (3, "golden:slim_L3_nonnested_k3", "fused"), (3, "golden:slim_L2_julia_quirks_k4", "fused"),
          (3, "decomposed-1000", "fused"), (3, "golden:wide_L3_banded_stale_k7", "fused-side"),
          (4, "L2", "fused"), (4, "small", "fused-side"), (4, "banded", "fused"), (4, "golden:slim_L4_nested_k6", "fused-side"),
-         (4, "golden:wide_L2_random_k5", "fused")]
+         (4, "golden:wide_L2_random_k5", "fused"),
+         (2, "local16", "fused"), (2, "local16", False), (4, "local16", "fused-side"), (4, "local16", True)]
 
 
 @pytest.mark.parametrize("world", [2, 3, 4])
@@ -308,3 +316,23 @@ def test_shard_local_matrices_are_valid_uploads(block_diagonal, band):
                     assert np.all(np.diff(sh.indptr) >= 0)
                     if sh.nnz:
                         assert sh.indices.min() >= 0 and sh.indices.max() < sh.local_rows
+
+
+def test_locality_partition_rules():
+    from arrow_matrix_b200 import decomp
+    w, nb, parts = 4, 8, 4
+    prev = np.array([0, 16, 32, 48, 64])                       # level above: 16 rows per GPU
+    ident = np.arange(nb * w)
+    # level rows map onto the first half of the level above, in order: blocks 0-3 -> GPU 0, 4-7 -> GPU 1
+    assert decomp.locality_partition(ident, nb, w, prev, parts).tolist() == [0, 4, 8, 8, 8]
+    # a uniformly random permutation keeps the even split
+    assert decomp.locality_partition(np.random.default_rng(0).permutation(64)[:32], nb, w, prev, parts) is None
+    # votes that are not monotone cannot give contiguous shards
+    rev = ident[::-1].copy()
+    assert decomp.locality_partition(rev + 32, nb, w, prev, parts) is None
+    # block-row 0 stays on GPU 0 even when its rows map elsewhere
+    shifted = np.concatenate([np.arange(48, 52), np.arange(4, 32)])
+    b = decomp.locality_partition(shifted, nb, w, prev, parts)
+    assert b is not None and b[1] >= 1
+    # one GPU would get everything: too skewed
+    assert decomp.locality_partition(ident % 16, nb, w, prev, parts, max_skew=2.0) is None
