@@ -125,6 +125,7 @@ struct arrow_ctx {
     int rows_per_group = 0;           // arrow_set_option(ARROW_OPT_ROWS_PER_GROUP): 0 = auto (pairs at k = 32), 1 / 2 forced
     int spmm_sm_limit = 0;            // arrow_set_option(ARROW_OPT_SPMM_SM_LIMIT): cap on the SMs a SpMM grid covers (0 = all)
     int clock_khz = 2000000;          // SM clock (kHz) for the barrier time-out
+    int force_skip_path = 0;          // arrow_set_option(ARROW_OPT_FORCE_PREDICATED): measurement switch
     int smem_carveout = -1;           // arrow_set_option(ARROW_OPT_SMEM_CARVEOUT): preferred shared-memory carve-out (percent) of the tile kernel
     int push_ctas = 0;                // arrow_set_option(ARROW_OPT_PUSH_CTAS): grid of the NVLink push kernel (0 = default)
     long long barrier_timeout_ms = 30000;   // arrow_set_option(ARROW_OPT_BARRIER_TIMEOUT_MS)
@@ -1608,6 +1609,7 @@ int arrow_set_option(arrow_ctx *ctx, int option, int value) {
             return ARROW_OK;
         case ARROW_OPT_ROWS_PER_GROUP: ctx->rows_per_group = (value == 1 || value == 2) ? value : 0; return ARROW_OK;
         case ARROW_OPT_SMEM_CARVEOUT: ctx->smem_carveout = value; return ARROW_OK;
+        case ARROW_OPT_FORCE_PREDICATED: ctx->force_skip_path = value ? 1 : 0; return ARROW_OK;
         case ARROW_OPT_SPMM_SM_LIMIT: ctx->spmm_sm_limit = value < 0 ? 0 : value; return ARROW_OK;
         case ARROW_OPT_PUSH_CTAS: ctx->push_ctas = value < 0 ? 0 : value; return ARROW_OK;
         case ARROW_OPT_BARRIER_TIMEOUT_MS: ctx->barrier_timeout_ms = value < 1 ? 1 : value; return ARROW_OK;
@@ -2233,7 +2235,7 @@ static int spmm_impl(arrow_ctx *ctx, const SpmmCall &q) {
             t.a = a;
             t.tiles = A->tiles;
             t.n_tiles = A->n_tiles;
-            t.skip = A->may_skip ? 1 : 0;
+            t.skip = (A->may_skip || ctx->force_skip_path) ? 1 : 0;
             t.ticket = ctx->tile_ticket + 2 * lane;
             t.l2_hints = (rm != nullptr || acc) ? ctx->l2_hints_fused : ctx->l2_hints_plain;
             t.prefetch = fused_launch ? ctx->prefetch_fused : ctx->prefetch_plain;
@@ -2712,6 +2714,13 @@ int arrow_lane_sync(arrow_ctx *ctx, int lane) {
     int rc = lane_stream(ctx, lane, &st);
     if (rc != ARROW_OK) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    int flag = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&flag, ctx->dev_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag != 0) {
+        ctx->poisoned = true;
+        return fail(ctx, ARROW_ERR_CUDA, "device-side failure flag %d: a peer barrier timed out after %lld ms; the context is "
+                    "poisoned (results after the time-out are racy) -- destroy it", flag, ctx->barrier_timeout_ms);
+    }
     return ARROW_OK;
 }
 

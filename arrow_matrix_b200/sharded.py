@@ -486,6 +486,11 @@ class ShardedArrowEngine:
         self.xi = [0] * self.L
         self.ci = [0] * self.L
         self._pair = 0                      # which level-0 pair is active: tile index = 2*pair + {0,1}
+        if self.fp is None and hasattr(be, "prepare_exchange"):
+            # exchange tables, identity maps, views: everything the step would otherwise create lazily.  Allocation and
+            # (above all) cudaFree synchronise the whole device; when the ranks are threads of one process that must not
+            # happen while a peer's barrier kernel is already spinning
+            be.prepare_exchange(self.L, [min(self.width, sh.rows_global) for sh in plan.levels])
         self.total_nnz_local = sum(sh.nnz for sh in plan.levels)
         self.total_nnz = int(be.allreduce_sum(self.total_nnz_local))
         self.local_rows = plan.levels[0].own_rows
@@ -1078,6 +1083,19 @@ class CudaPeerBackend:
                      unpack=self.ctx.map_upload(raw["unpack"], max(n_recv, 1)))
             self._xtab[key] = t
         return t
+
+    def prepare_exchange(self, L: int, head_rows):
+        if self.plan is not None:
+            for lvl in range(L):
+                if lvl > 0:
+                    self._exchange_table(lvl, True)
+                if lvl < L - 1:
+                    self._exchange_table(lvl, False)
+        if self.rank == 0:
+            for rows in set(int(r) for r in head_rows):
+                if rows not in self._ident:
+                    self._ident[rows] = self.ctx.map_upload(np.arange(rows, dtype=np.int64), rows)
+        self.ctx.sync()
 
     def _raw_view(self, g: int, float_off: int, rows: int):
         key = ("raw", g, float_off, rows)

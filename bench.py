@@ -48,6 +48,12 @@ def parse():
     ap.add_argument("--k", type=int, default=128)
     ap.add_argument("--levels", type=int, default=2)
     ap.add_argument("--perm", type=str, default="random", choices=["random", "local", "identity"])
+    ap.add_argument("--workload", type=str, default="g2", choices=["g2", "ba"],
+                    help="g2 = the synthetic arrow decomposition of SURVEY 8d (default, BASELINE.json's workload); ba = a "
+                         "Barabasi-Albert graph run through this repository's arrow decomposition (the reference's own "
+                         "synthetic route, arrow_bench.py:24-41): skewed degrees, hub rows, a dense head")
+    ap.add_argument("--vertices", type=int, default=1000000, help="--workload ba: vertices")
+    ap.add_argument("--ba-m", type=int, default=5, help="--workload ba: edges per new vertex")
     ap.add_argument("--mode", type=str, default="auto", choices=["auto", "fused", "exchange"])
     ap.add_argument("--exchange", type=str, default="p2p", choices=["p2p", "p2p-direct", "nccl"],
                     help="multi-GPU exchange-mode transport (mode=exchange): NVLink peer pulls (default) or NCCL all-to-all")
@@ -118,12 +124,20 @@ class ClockSampler:
 
 
 def workload_name(a):
+    if a.workload == "ba":
+        return (f"Barabasi-Albert graph, {a.vertices} vertices, m={a.ba_m} (seed 503) -> arrow decomposition of this repository, "
+                f"width {a.width}, at most {a.levels} levels, k={a.k} fp32")
     return (f"G2 synthetic arrow decomposition: {a.blocks * a.width} rows, width {a.width}, {a.levels} levels, "
             f"~10 nnz/row, k={a.k} fp32, level-1 permutation {a.perm} (seed 503)")
 
 
 def build_decomposition(a, blocks=None):
     from arrow_matrix_b200 import synth
+    if a.workload == "ba":
+        from arrow_matrix_b200.decomposition import arrow_decomposition
+        n = a.vertices if blocks is None else min(a.vertices, blocks * a.width)
+        A = synth.barabasi_albert(n, a.ba_m, seed=503)
+        return arrow_decomposition(A, a.width, max_number_of_levels=a.levels, block_diagonal=True, seed=1)
     return synth.synth_decomposition(blocks or a.blocks, a.width, levels=a.levels, perm_kind=a.perm, seed=503)
 
 
@@ -414,7 +428,8 @@ def run_b200(a):
     t_setup = time.time()
     comm = comm_mod.world_comm()
     # the public path: files on disk -> load_decomposition_new -> initialize -> load blocks (every rank maps the same files)
-    base = os.path.join(ROOT, "tmp", f"bench_{a.blocks}_{a.width}_{a.levels}_{a.perm}")
+    tag = f"ba_{a.vertices}_{a.ba_m}" if a.workload == "ba" else f"{a.blocks}_{a.perm}"
+    base = os.path.join(ROOT, "tmp", f"bench_{tag}_{a.width}_{a.levels}")
     if rank == 0:
         dec0 = build_decomposition(a)
         graphio.save_decomposition_new(dec0, base, a.width, block_diagonal=True)

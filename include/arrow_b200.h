@@ -80,6 +80,7 @@ int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segme
 #define ARROW_OPT_PUSH_CTAS       8   /* grid of arrow_push_rows (0 = 2 per SM) */
 #define ARROW_OPT_SMEM_CARVEOUT  10   /* preferred shared-memory carve-out (percent, -1 = driver default) of the tile kernel: the rest of
                                         the SM's 228 KB is L1, the landing buffer of the gathers in flight (measurement switch) */
+#define ARROW_OPT_FORCE_PREDICATED 11  /* 1: the tile kernel takes its predicated gather path even when every column is valid (measurement switch) */
 #define ARROW_OPT_BARRIER_TIMEOUT_MS 9 /* arrow_peer_barrier gives up after this long (default 30000) and poisons the context */
 int  arrow_set_option(arrow_ctx *ctx, int option, int value);
 
