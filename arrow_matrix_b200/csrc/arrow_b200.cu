@@ -125,6 +125,7 @@ struct arrow_ctx {
     int rows_per_group = 0;           // arrow_set_option(ARROW_OPT_ROWS_PER_GROUP): 0 = auto (pairs at k = 32), 1 / 2 forced
     int spmm_sm_limit = 0;            // arrow_set_option(ARROW_OPT_SPMM_SM_LIMIT): cap on the SMs a SpMM grid covers (0 = all)
     int clock_khz = 2000000;          // SM clock (kHz) for the barrier time-out
+    int tile_kernel = 1;              // arrow_set_option(ARROW_OPT_TILE_KERNEL): 1 = round-1 kernel for the launches it covers, 0 = generalised kernel everywhere
     int force_skip_path = 0;          // arrow_set_option(ARROW_OPT_FORCE_PREDICATED): measurement switch
     int smem_carveout = -1;           // arrow_set_option(ARROW_OPT_SMEM_CARVEOUT): preferred shared-memory carve-out (percent) of the tile kernel
     int push_ctas = 0;                // arrow_set_option(ARROW_OPT_PUSH_CTAS): grid of the NVLink push kernel (0 = default)
@@ -676,6 +677,192 @@ struct TileArgs {
 __device__ __forceinline__ void bulk_prefetch_l2(const void *gptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
+// ------------------------------------------------------------------------------------------------
+// The round-1 tile kernel, verbatim (one row per lane group, identity / row-map output, no dual operand): kept as the
+// production path of those launches.  The generalised kernel below produces the same numbers but its fused level-1
+// launch (scattered first-touch gathers, latency bound) measured 2.2-2.6 ms against 1.8 ms for this code on the same GPU
+// (profiles/r02_kernel_sweep.md, section 5); ARROW_OPT_TILE_KERNEL switches between the two.
+// ------------------------------------------------------------------------------------------------
+template <int G, int VPL, bool ROWMAP, bool ACC, int TR, int TN>
+__global__ void __launch_bounds__(TILE_THREADS, 4) k_spmm_tiles_v1(TileArgs t) {
+    constexpr int TILE_PTR_WORDS = TileCfg<TR, TN>::PTR_WORDS;
+    constexpr int TILE_NNZ_WORDS = TileCfg<TR, TN>::NNZ_WORDS;
+    constexpr int TILE_STAGE_WORDS = TileCfg<TR, TN>::STAGE_WORDS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    int *stage_base = reinterpret_cast<int *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)2 * TILE_STAGE_WORDS * 4);
+    const SpmmArgs &a = t.a;
+    constexpr int RPW = 32 / G;
+    constexpr int UNROLL = (VPL >= 4) ? 2 : (VPL == 2 ? 4 : 8);
+    constexpr int TAIL = (UNROLL >= 4) ? UNROLL / 2 : UNROLL;     // predicated tail batches
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const bool EXACT = (t.a.k4 == G * VPL);                       // every lane owns valid columns
+    const int gl = lane % G;
+    const int gi = lane / G;
+    const int k4 = a.k4;
+    const float4 *__restrict__ Xl = reinterpret_cast<const float4 *>(a.X) + gl;
+    float4 *__restrict__ Cl = reinterpret_cast<float4 *>(a.C) + gl;
+    const uint64_t pol_keep = (t.l2_hints & 1) ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const uint64_t pol_stream = (t.l2_hints & 2) ? l2_policy_evict_first() : l2_policy_evict_normal();
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto prefetch = [&](int tile, int st) {
+        const int4 d = __ldg(t.tiles + tile);
+        const int rb4 = d.x & ~3;
+        const int a0 = d.z & ~3;
+        const uint32_t ptr_bytes = (uint32_t)(((d.y - rb4 + 1) + 3) & ~3) * 4u;
+        const uint32_t nnz_bytes = (uint32_t)(((d.w - a0) + 3) & ~3) * 4u;
+        int *sp = stage_base + (size_t)st * TILE_STAGE_WORDS;
+        mbar_expect_tx(&bars[st], ptr_bytes + 2u * nnz_bytes);
+        bulk_g2s_hint(sp, a.indptr + rb4, ptr_bytes, &bars[st], pol_stream);
+        if (nnz_bytes) {
+            bulk_g2s_hint(sp + TILE_PTR_WORDS, a.indices + a0, nnz_bytes, &bars[st], pol_stream);
+            bulk_g2s_hint(sp + TILE_PTR_WORDS + TILE_NNZ_WORDS, a.vals + a0, nnz_bytes, &bars[st], pol_stream);
+        }
+    };
+
+    // Dynamic scheduling: the first tile is blockIdx.x, every further tile comes from an atomic ticket.  All CTAs
+    // therefore work on one compact, moving window of ~gridDim.x consecutive tiles; a static round-robin lets
+    // CTAs drift apart over the ~260 tiles each one processes at 10M rows and the live X panels fall out of L2
+    // (measured: 62 % L2 hit rate, DRAM traffic 1.30x algorithmic before this change).
+    __shared__ int s_next[2];
+    uint32_t parity0 = 0u, parity1 = 0u;
+    int tile = blockIdx.x;
+    int st = 0;
+    if (tile < t.n_tiles && threadIdx.x == 0) prefetch(tile, 0);
+    for (; tile < t.n_tiles; st ^= 1) {
+        if (threadIdx.x == 0) {
+            const int next = atomicAdd(t.ticket, 1) + (int)gridDim.x;
+            s_next[st] = next;
+            if (next < t.n_tiles) prefetch(next, st ^ 1);
+        }
+        const int4 d = __ldg(t.tiles + tile);
+        if (st == 0) { mbar_wait(&bars[0], parity0); parity0 ^= 1u; }
+        else         { mbar_wait(&bars[1], parity1); parity1 ^= 1u; }
+        const int *sp = stage_base + (size_t)st * TILE_STAGE_WORDS;
+        const int *s_ptr = sp + (d.x - (d.x & ~3));
+        const int a0 = d.z & ~3;
+        const int *s_idx = sp + TILE_PTR_WORDS - a0;                    // index with global nnz offsets
+        const float *s_val = reinterpret_cast<const float *>(sp + TILE_PTR_WORDS + TILE_NNZ_WORDS) - a0;
+        const int n_rows_tile = d.y - d.x;
+
+        for (int lr = warp * RPW + gi; lr < n_rows_tile; lr += (TILE_THREADS / 32) * RPW) {
+            const int s = s_ptr[lr];
+            const int e = s_ptr[lr + 1];
+            if (e - s > a.long_threshold) continue;
+            const long long row = (long long)d.x + lr;
+            long long orow = row;
+            if (ROWMAP) {
+                orow = __ldg(a.rowmap + row);
+                if (orow < 0) continue;
+            }
+            if (false && t.prefetch) {
+                // software prefetch into L2: the X rows the group's NEXT row of this tile will gather (their column
+                // indices are already in shared memory); hides DRAM latency of first-touch / scattered rows
+                const int nlr = lr + (TILE_THREADS / 32) * RPW;
+                if (nlr < n_rows_tile) {
+                    const int ns = s_ptr[nlr], ne = s_ptr[nlr + 1];
+                    if (ne - ns <= a.long_threshold) {
+                        const int lines = (a.k * 4 + 127) >> 7;
+                        for (int q = ns + gl; q < ne; q += G) {
+                            const int cq = s_idx[q];
+                            if (cq >= 0) {
+                                const char *xr = reinterpret_cast<const char *>(a.X) + (long long)cq * a.k * 4;
+                                for (int l = 0; l < lines; ++l)
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + l * 128));
+                            }
+                        }
+                    }
+                }
+            }
+            // accumulate mode: the old C row is read FIRST so that its latency hides behind the gathers (only this
+            // group ever touches the row: the row maps are injective)
+            float4 acc[VPL];
+            float4 *cr = Cl + orow * k4;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+                acc[i] = (ACC && gl + i * G < k4) ? ld_f4_hint(cr + i * G, pol_stream) : f4_zero();
+            if (a.add_map != nullptr) {
+                // epilogue gather-add, issued first so its latency hides behind the gathers: the backward exchange
+                // C_{j-1}[to_prev[r]] += C_j[r] (arrow_dec_mpi.py:437) seen from the receiving row
+                const int am = __ldg(a.add_map + row);
+                if (am >= 0) {
+                    const float4 *ar = reinterpret_cast<const float4 *>(a.add_src) + (long long)am * k4 + gl;
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i)
+                        if (gl + i * G < k4) f4_add(acc[i], ld_f4_hint(ar + i * G, pol_stream));
+                }
+            }
+            int p = s;
+            if (EXACT && !t.skip) {
+                // unpredicated batches: full UNROLL batches, then the remainder as 4 / 2 / 1 (binary decomposition) --
+                // a predicated tail batch costs as many instructions as a full one
+                auto batch = [&](auto n_tag) {
+                    constexpr int N = decltype(n_tag)::value;
+                    int c[N];
+                    float v[N];
+#pragma unroll
+                    for (int u = 0; u < N; ++u) {
+                        c[u] = s_idx[p + u];
+                        v[u] = s_val[p + u];
+                    }
+                    float4 x[N][VPL];
+#pragma unroll
+                    for (int u = 0; u < N; ++u) {
+                        const float4 *xr = Xl + (long long)c[u] * k4;
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) x[u][i] = ldg_f4_hint(xr + i * G, pol_keep);
+                    }
+#pragma unroll
+                    for (int u = 0; u < N; ++u)
+#pragma unroll
+                        for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
+                    p += N;
+                };
+                while (p + UNROLL <= e) batch(std::integral_constant<int, UNROLL>{});
+                if constexpr (UNROLL >= 8) { if (e - p >= 4) batch(std::integral_constant<int, 4>{}); }
+                if constexpr (UNROLL >= 4) { if (e - p >= 2) batch(std::integral_constant<int, 2>{}); }
+                if (e - p >= 1) batch(std::integral_constant<int, 1>{});
+            }
+            // tail (and the general case): predicated batches of TAIL
+            for (; p < e; p += TAIL) {
+                int c[TAIL];
+                float v[TAIL];
+#pragma unroll
+                for (int u = 0; u < TAIL; ++u) {
+                    const bool ok = p + u < e;
+                    c[u] = ok ? s_idx[p + u] : -1;
+                    v[u] = ok ? s_val[p + u] : 0.f;
+                }
+                float4 x[TAIL][VPL];
+#pragma unroll
+                for (int u = 0; u < TAIL; ++u) {
+                    const float4 *xr = Xl + (long long)c[u] * k4;
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i)
+                        x[u][i] = (c[u] >= 0 && gl + i * G < k4) ? ldg_f4_hint(xr + i * G, pol_keep) : f4_zero();
+                }
+#pragma unroll
+                for (int u = 0; u < TAIL; ++u)
+#pragma unroll
+                    for (int i = 0; i < VPL; ++i) f4_fma(acc[i], v[u], x[u][i]);
+            }
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+                if (gl + i * G < k4) st_f4_hint(cr + i * G, acc[i], pol_stream);
+        }
+        __syncthreads();            // stage `st` may be refilled by the next iteration's prefetch
+        tile = s_next[st];
+    }
+}
+
 // G lanes own a row (VPL float4 each).  RPG = 2: a group works on two rows at once (rows lr and lr + rows-per-pass) with
 // half the batch size per row: the gathers of both rows are issued before either row's FMAs.  Same registers, but the
 // short tail batch of one row (a 10-entry row is 8 + 2 gathers: the second round trip keeps 2 of 8 slots busy) overlaps
@@ -1405,6 +1592,29 @@ int launch_tiles_one(arrow_ctx *ctx, const TileArgs &t) {
     return ARROW_OK;
 }
 
+template <int G, int VPL, bool ROWMAP, bool ACC, int TR, int TN>
+int launch_tiles_v1(arrow_ctx *ctx, const TileArgs &t) {
+    constexpr size_t SMEM = TileCfg<TR, TN>::SMEM_BYTES;
+    auto fn = k_spmm_tiles_v1<G, VPL, ROWMAP, ACC, TR, TN>;
+    static bool attr_set[64] = {};
+    static int occ_dev[64] = {};
+    const int dv = ctx->device & 63;
+    if (!attr_set[dv]) {
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dev[dv], fn, TILE_THREADS, SMEM) != cudaSuccess || occ_dev[dv] < 1) occ_dev[dv] = 1;
+        attr_set[dv] = true;
+    }
+    const int occ = occ_dev[dv];
+    const int per_sm = (ctx->spmm_ctas_per_sm > 0) ? std::min(occ, ctx->spmm_ctas_per_sm) : occ;
+    int sms = ctx->sm_count;
+    if (ctx->spmm_sm_limit > 0) sms = std::min(sms, ctx->spmm_sm_limit);
+    int grid = (int)std::min<long long>((long long)per_sm * sms, t.n_tiles);
+    cudaMemsetAsync(t.ticket, 0, sizeof(int), cur_stream(ctx));      // this kernel does not re-arm its scheduler itself
+    fn<<<grid, TILE_THREADS, SMEM, cur_stream(ctx)>>>(t);
+    ctx->launches++;
+    return ARROW_OK;
+}
+
 template <int G, int VPL, int TR, int TN, int RPG, int MINB>
 int launch_tiles_gv(arrow_ctx *ctx, const TileArgs &t, const TileLaunch &L) {
     if (L.out_mode == OUT_ROWPTR) {
@@ -1423,6 +1633,12 @@ int launch_tiles_gv(arrow_ctx *ctx, const TileArgs &t, const TileLaunch &L) {
         return launch_tiles_gv<G, VPL, TR, TN, 1, 4>(ctx, t, L);
     } else {
         const bool rowmap = L.out_mode == OUT_ROWMAP;
+        if (ctx->tile_kernel == 1) {
+            if (rowmap && L.acc) return launch_tiles_v1<G, VPL, true, true, TR, TN>(ctx, t);
+            if (rowmap) return launch_tiles_v1<G, VPL, true, false, TR, TN>(ctx, t);
+            if (L.acc) return launch_tiles_v1<G, VPL, false, true, TR, TN>(ctx, t);
+            return launch_tiles_v1<G, VPL, false, false, TR, TN>(ctx, t);
+        }
         if (rowmap && L.acc) return launch_tiles_one<G, VPL, OUT_ROWMAP, true, TR, TN, 1, MINB, false>(ctx, t);
         if (rowmap) return launch_tiles_one<G, VPL, OUT_ROWMAP, false, TR, TN, 1, MINB, false>(ctx, t);
         if (L.acc) return launch_tiles_one<G, VPL, OUT_IDENTITY, true, TR, TN, 1, MINB, false>(ctx, t);
@@ -1610,6 +1826,7 @@ int arrow_set_option(arrow_ctx *ctx, int option, int value) {
         case ARROW_OPT_ROWS_PER_GROUP: ctx->rows_per_group = (value == 1 || value == 2) ? value : 0; return ARROW_OK;
         case ARROW_OPT_SMEM_CARVEOUT: ctx->smem_carveout = value; return ARROW_OK;
         case ARROW_OPT_FORCE_PREDICATED: ctx->force_skip_path = value ? 1 : 0; return ARROW_OK;
+        case ARROW_OPT_TILE_KERNEL: ctx->tile_kernel = value ? 1 : 0; return ARROW_OK;
         case ARROW_OPT_SPMM_SM_LIMIT: ctx->spmm_sm_limit = value < 0 ? 0 : value; return ARROW_OK;
         case ARROW_OPT_PUSH_CTAS: ctx->push_ctas = value < 0 ? 0 : value; return ARROW_OK;
         case ARROW_OPT_BARRIER_TIMEOUT_MS: ctx->barrier_timeout_ms = value < 1 ? 1 : value; return ARROW_OK;

@@ -31,12 +31,15 @@ def timed(fn, iters=10):
     return ctx.timer_ms(3) / iters
 
 
-for forced in (0, 1):
-    ctx.set_option(ctx.OPT_FORCE_PREDICATED, forced)
-    for hints in (3, 0):
-        ctx.set_option(ctx.OPT_L2_HINTS_PLAIN, hints)
+for kernel in (1, 0):
+    ctx.set_option(ctx.OPT_TILE_KERNEL, kernel)
+    for forced in (0, 1):
+        ctx.set_option(ctx.OPT_FORCE_PREDICATED, forced)
         ms1 = timed(lambda: ctx.spmm(st1.csr_fused, x, st1.cbuf))
         ms0 = timed(lambda: ctx.spmm_add(st0.csr, x, out, st1.cbuf, st1.to_next_dev))
-        print(json.dumps({"k": k, "predicated": forced, "l2_hints_plain": hints, "level1_ms": round(ms1, 4), "level0_add_ms": round(ms0, 4)}), flush=True)
+        eng.rewind_features()
+        ms = timed(eng.step)
+        print(json.dumps({"k": k, "tile_kernel": "round-1" if kernel else "generalised", "predicated": forced, "level1_ms": round(ms1, 4),
+                          "level0_add_ms": round(ms0, 4), "step_ms": round(ms, 4)}), flush=True)
 ctx.set_option(ctx.OPT_FORCE_PREDICATED, 0)
-ctx.set_option(ctx.OPT_L2_HINTS_PLAIN, 3)
+ctx.set_option(ctx.OPT_TILE_KERNEL, 1)
