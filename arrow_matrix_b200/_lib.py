@@ -34,7 +34,7 @@ EXPORTS = [
     "arrow_timer_start", "arrow_timer_stop", "arrow_timer_elapsed_ms", "arrow_launch_count", "arrow_l2_flush",
     "arrow_ptrtable_upload", "arrow_ptrtable_free", "arrow_spmm_ex", "arrow_push_rows", "arrow_reduce_rows",
     "arrow_graph_begin", "arrow_graph_end", "arrow_graph_launch", "arrow_graph_free",
-    "arrow_host_alloc_numa", "arrow_bind_thread_to_device_numa",
+    "arrow_host_alloc_numa", "arrow_bind_thread_to_device_numa", "arrow_preload_kernels",
 ]
 ABI_VERSION = 2          # ARROW_ABI_VERSION of include/arrow_b200.h this binding was written against
 
@@ -127,6 +127,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         "arrow_graph_free": (c_int, [P, I]),
         "arrow_host_alloc_numa": (c_int, [c_size_t, I, POINTER(P)]),
         "arrow_bind_thread_to_device_numa": (c_int, [I, pI, pI]),
+        "arrow_preload_kernels": (c_int, [P, I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = the .so does not export a declared symbol
@@ -211,6 +212,10 @@ class Context:
 
     def sync(self):
         self._check(self.lib.arrow_sync(self._h))
+
+    def preload_kernels(self, k: int):
+        """load every kernel a step with ``k`` feature columns can launch, before any peer barrier is in flight"""
+        self._check(self.lib.arrow_preload_kernels(self._h, int(k)))
 
     def device_info(self):
         sm, fr, tot = c_int(), c_int64(), c_int64()

@@ -50,6 +50,7 @@ class CudaHaloFabric:
     def alloc(self, rows: Dict[str, int], k: int):
         ctx = self.ctx
         self.k = int(k)
+        ctx.preload_kernels(self.k)        # nothing may be loaded for the first time while a peer barrier spins
         offs, pos = {}, 128
         for name, r in rows.items():
             offs[name] = pos

@@ -3128,6 +3128,92 @@ int arrow_launch_count(arrow_ctx *ctx, int64_t *count) {
     return ARROW_OK;
 }
 
+// Lazy module loading (the CUDA default) loads a kernel at its first launch, and loading synchronises the context.  A
+// kernel that spin-waits -- arrow_peer_barrier on one lane -- while another lane (or, with rank threads, another
+// rank) launches a kernel for the first time therefore deadlocks until the barrier times out.  This runs every kernel
+// the step of a given feature width can launch once, on tiny operands, before any barrier is in flight.
+int arrow_preload_kernels(arrow_ctx *ctx, int k) {
+    CHECK_CTX(ctx);
+    if (k < 1) return fail(ctx, ARROW_ERR_ARG, "k must be positive");
+    const int64_t n = 700;
+    std::vector<int32_t> ip(n + 1), ix;
+    std::vector<float> val;
+    for (int64_t r = 0; r < n; ++r) {
+        ip[r] = (int32_t)ix.size();
+        const int len = (r == 3) ? 600 : 3;                       // one long row: the segmented kernels load too
+        for (int j = 0; j < len; ++j) { ix.push_back((int32_t)((r * 7 + j) % n)); val.push_back(1.0f); }
+        std::sort(ix.begin() + ip[r], ix.end());
+        ix.erase(std::unique(ix.begin() + ip[r], ix.end()), ix.end());
+        val.resize(ix.size());
+    }
+    ip[n] = (int32_t)ix.size();
+    int csr = -1, x = -1, x2 = -1, c = -1, c2 = -1, map = -1, tab = -1, rc = ARROW_OK;
+    std::vector<int64_t> ident(n);
+    for (int64_t i = 0; i < n; ++i) ident[i] = i;
+    std::vector<int32_t> which(n, 0);
+    const int saved_kernel = ctx->tile_kernel, saved_lane = ctx->cur_lane;
+    ctx->cur_lane = 0;
+#define PRE(expr) do { if (rc == ARROW_OK) rc = (expr); } while (0)
+    PRE(arrow_csr_upload(ctx, n, n, (int64_t)ix.size(), ip.data(), 4, ix.data(), 4, val.data(), &csr));
+    PRE(arrow_dense_alloc(ctx, n, k, &x));
+    PRE(arrow_dense_alloc(ctx, n, k, &x2));
+    PRE(arrow_dense_alloc(ctx, n, k, &c));
+    PRE(arrow_dense_alloc(ctx, n, k, &c2));
+    PRE(arrow_map_upload(ctx, ident.data(), n, n, &map));
+    if (rc == ARROW_OK) { const int tiles[1] = {c2}; rc = arrow_ptrtable_upload(ctx, tiles, 1, which.data(), ident.data(), n, &tab); }
+    for (int tk = 0; tk < 2 && rc == ARROW_OK; ++tk) {
+        ctx->tile_kernel = tk;
+        for (int rpg = 1; rpg <= 2; ++rpg) {
+            const int variant = ARROW_VARIANT_TILES | (rpg << 8);
+            PRE(arrow_spmm(ctx, csr, x, c, -1, 0, variant));
+            PRE(arrow_spmm(ctx, csr, x, c, -1, ARROW_ACCUMULATE, variant));
+            PRE(arrow_spmm(ctx, csr, x, c, map, 0, variant));
+            PRE(arrow_spmm(ctx, csr, x, c, map, ARROW_ACCUMULATE, variant));
+            PRE(arrow_spmm_add(ctx, csr, x, c, c2, map, variant));
+            PRE(arrow_spmm_ex(ctx, csr, x, x2, n / 2, c, -1, -1, -1, variant));
+            PRE(arrow_spmm_ex(ctx, csr, x, x2, n / 2, -1, tab, -1, -1, variant));
+            PRE(arrow_spmm_ex(ctx, csr, x, -1, 0, -1, tab, c, map, variant));
+        }
+    }
+    ctx->tile_kernel = saved_kernel;
+    PRE(arrow_gather_rows(ctx, c, x, map, 0));
+    PRE(arrow_gather_rows(ctx, c, x, map, ARROW_ACCUMULATE));
+    if (rc == ARROW_OK) {
+        const int srcs[1] = {x};
+        const int64_t bounds[2] = {0, n};
+        PRE(arrow_gather_rows_multi(ctx, c, srcs, bounds, 1, map, 0));
+        PRE(arrow_gather_rows_multi(ctx, c, srcs, bounds, 1, map, ARROW_ACCUMULATE));
+        const int dsts[1] = {c};
+        PRE(arrow_push_rows(ctx, dsts, bounds, 1, x, map));
+        PRE(arrow_reduce_rows(ctx, c, -1, srcs, 1, n));
+        PRE(arrow_reduce_rows(ctx, -1, tab, srcs, 1, n));
+        PRE(arrow_dense_fill(ctx, c, 1.0f));
+        // the barrier kernel against this context's own flag word (world of one): loads it, never waits
+        const int flags[1] = {c};
+        for (int lane = 0; lane < ARROW_N_LANES && rc == ARROW_OK; lane += ARROW_LANE_SIDE) {
+            cudaStream_t st;
+            rc = lane_stream(ctx, lane, &st);
+            ctx->cur_lane = lane;
+            if (lane) PRE(arrow_lane_wait(ctx, lane, 0));
+            PRE(arrow_dense_fill(ctx, c, 0.0f));
+            PRE(arrow_peer_barrier(ctx, flags, 0, 1));
+            if (lane) PRE(arrow_lane_wait(ctx, 0, lane));
+        }
+    }
+#undef PRE
+    ctx->cur_lane = saved_lane;
+    cudaStreamSynchronize(ctx->stream);
+    for (int l = 1; l < ARROW_N_LANES; ++l)
+        if (ctx->lanes[l]) cudaStreamSynchronize(ctx->lanes[l]);
+    if (tab >= 0) arrow_ptrtable_free(ctx, tab);
+    if (map >= 0) arrow_map_free(ctx, map);
+    for (int h : {x, x2, c, c2}) if (h >= 0) arrow_dense_free(ctx, h);
+    if (csr >= 0) arrow_csr_free(ctx, csr);
+    // the barrier test bumped the epoch counters of a flag word that no longer exists: start clean
+    cudaMemset(ctx->barrier_epoch, 0, ARROW_N_LANES * sizeof(unsigned int));
+    return rc;
+}
+
 int arrow_l2_flush(arrow_ctx *ctx) {
     CHECK_CTX(ctx);
     const size_t bytes = (size_t)256 << 20;      // 256 MiB > 126 MB of L2

@@ -902,6 +902,7 @@ class CudaPeerBackend:
         self.comm = comm
         self.rank, self.world = comm.Get_rank(), comm.Get_size()
         self.ctx = _lib.Context(device, stream)
+        self._preloaded = set()
         self._tiles = None
         self._peer = None         # [rank][level][which] -> Dense (imported or own)
         self._flags = None
@@ -941,6 +942,11 @@ class CudaPeerBackend:
         """One arena per rank (a single cudaMalloc => a single IPC handle): ping-pong tiles per level + flags."""
         ctx = self.ctx
         self.k = k
+        if k not in self._preloaded:
+            # no kernel may be loaded for the first time while a peer barrier spins (lazy module loading synchronises
+            # the context): load everything this feature width can launch now
+            ctx.preload_kernels(k)
+            self._preloaded.add(k)
         tiles_per_level = list(tiles_per_level) if tiles_per_level is not None else [2] * len(rows_per_level)
         align = 64                                              # floats (256 bytes)
         offs, pos = [], 128                                     # first 128 floats: barrier flags of the two lanes

@@ -230,6 +230,12 @@ int  arrow_timer_elapsed_ms(arrow_ctx *ctx, int slot, float *ms);   /* synchroni
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int  arrow_launch_count(arrow_ctx *ctx, int64_t *count);
 
+/* Run every kernel a step with `k` feature columns can launch once, on tiny operands.  CUDA loads a kernel lazily at
+ * its first launch and loading synchronises the context: if that happens while arrow_peer_barrier spins on another lane
+ * (or, with several rank threads in one process, in another rank) the step hangs until the barrier times out.  Call it
+ * after arrow_ctx_create, before the first barrier -- or start the process with CUDA_MODULE_LOADING=EAGER. */
+int  arrow_preload_kernels(arrow_ctx *ctx, int k);
+
 /* measurement helpers used by bench.py: write `bytes` of scratch (L2 flush) */
 int  arrow_l2_flush(arrow_ctx *ctx);
 
