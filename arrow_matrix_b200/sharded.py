@@ -802,6 +802,10 @@ class ShardedArrowEngine:
                 g = ctx.graph_end()
             self.graphs[key] = g
             self.xi, self.ci = xi, ci
+            # instantiating a graph allocates (and may synchronise the device); with rank threads sharing one device
+            # context that must not overlap a peer's replay, whose first kernel is a spinning barrier: every rank
+            # finishes its instantiation before anyone launches
+            self.be.comm.Barrier()
         ctx.graph_launch(g)
         out0 = self._other(0, self.xi[0])
         self.ci[0] = out0
