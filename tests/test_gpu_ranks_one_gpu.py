@@ -62,14 +62,19 @@ CASES = {"L2k128": (128, 9, 128, 2, True, False), "L2k16": (64, 12, 16, 2, True,
          "L2k5": (32, 7, 5, 2, True, False)}
 
 
-@pytest.mark.parametrize("schedule", ["fused", "fused+side", "fused+side+graph", "exchange", "exchange+overlap", "exchange+overlap2",
-                                      "p2p-direct"])
-@pytest.mark.parametrize("case", list(CASES))
-@pytest.mark.parametrize("world", [2, 3])
+# (world, case, schedule): every schedule on the headline shape, every shape through the fused step with graph replay, the
+# exchange-mode fall-backs where they matter (stale rows, banded halos)
+MATRIX = [(2, "L2k128", s) for s in ("fused", "fused+side", "fused+side+graph", "exchange", "exchange+overlap", "exchange+overlap2",
+                                     "p2p-direct")] + \
+         [(3, c, "fused+side+graph") for c in CASES] + \
+         [(2, "L2k16", "fused+side"), (2, "L3k16", "fused"), (3, "L4k8", "fused"), (2, "L2k5", "fused+side+graph"),
+          (2, "L3stale_k6", "exchange+overlap"), (3, "L3stale_k6", "p2p-direct"), (2, "banded_k8", "fused+side"),
+          (3, "banded_k8", "exchange"), (4, "L2k16", "fused+side+graph"), (4, "banded_k8", "fused")]
+
+
+@pytest.mark.parametrize("world,case,schedule", MATRIX)
 def test_rank_threads_match_protocol_oracle(cuda_device, world, case, schedule):
     w, t0, k, levels, nested, banded = CASES[case]
-    if world == 3 and case in ("L2k128", "L4k8") and "graph" not in schedule and schedule != "fused":
-        pytest.skip("covered at world 2")
     dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind="random", seed=31, nested=nested, hub_rows=2, hub_nnz=600,
                                     band_nnz=4 if banded else 0, shrink=1 if banded else 2)
     po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=not banded)
