@@ -1587,6 +1587,9 @@ int launch_tiles_one(arrow_ctx *ctx, const TileArgs &t) {
     int sms = ctx->sm_count;
     if (ctx->spmm_sm_limit > 0) sms = std::min(sms, ctx->spmm_sm_limit);
     int grid = (int)std::min<long long>((long long)per_sm * sms, t.n_tiles);
+    // the scheduler words are zeroed before every launch: the round-1 kernel (which shares them) leaves its ticket behind,
+    // and a launch must never depend on how the previous one on this lane ended
+    cudaMemsetAsync(t.ticket, 0, 2 * sizeof(int), cur_stream(ctx));
     fn<<<grid, TILE_THREADS, SMEM, cur_stream(ctx)>>>(t);
     ctx->launches++;
     return ARROW_OK;
@@ -1609,7 +1612,7 @@ int launch_tiles_v1(arrow_ctx *ctx, const TileArgs &t) {
     int sms = ctx->sm_count;
     if (ctx->spmm_sm_limit > 0) sms = std::min(sms, ctx->spmm_sm_limit);
     int grid = (int)std::min<long long>((long long)per_sm * sms, t.n_tiles);
-    cudaMemsetAsync(t.ticket, 0, sizeof(int), cur_stream(ctx));      // this kernel does not re-arm its scheduler itself
+    cudaMemsetAsync(t.ticket, 0, 2 * sizeof(int), cur_stream(ctx));
     fn<<<grid, TILE_THREADS, SMEM, cur_stream(ctx)>>>(t);
     ctx->launches++;
     return ARROW_OK;

@@ -21,6 +21,7 @@ peer memory through CUDA IPC) here, a gloo/numpy stand-in in ``tests/`` for the 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -907,10 +908,30 @@ class CudaPeerBackend:
         self.rank, self.world = comm.Get_rank(), comm.Get_size()
         self.ctx = _lib.Context(device, stream)
         self._preloaded = set()
+        if os.environ.get("ARROW_DEBUG_SYNC") == "1":
+            self._wrap_debug_sync()
         self._tiles = None
         self._peer = None         # [rank][level][which] -> Dense (imported or own)
         self._flags = None
         self._ident = {}
+
+    def _wrap_debug_sync(self):
+        """ARROW_DEBUG_SYNC=1: synchronise after every backend operation so that an asynchronous CUDA error is reported by
+        the operation that caused it (debugging aid; serialises the lanes)"""
+        import functools
+        for name in ("spmm", "barrier", "pull_rows", "bcast_head", "reduce_head", "copy_rows_from_peer", "push", "spmm_fused",
+                     "reduce_rows", "final_add", "stage_rows", "apply_staged"):
+            fn = getattr(self, name)
+
+            def wrapped(*a, _fn=fn, _name=name, **kw):
+                out = _fn(*a, **kw)
+                try:
+                    for lane in (3, 0):
+                        self.ctx.lane_sync(lane)
+                except Exception as e:      # noqa: BLE001
+                    raise RuntimeError(f"rank {self.rank}: CUDA error surfaced right after backend.{_name}{a}: {e}") from e
+                return out
+            setattr(self, name, functools.wraps(fn)(wrapped))
 
     def close(self):
         """Collective.  An exported arena must outlive every peer's mapping of it (CUDA IPC): all ranks finish their
