@@ -81,7 +81,11 @@ class TorchComm:
 class ThreadWorld:
     """Shared state of ``n`` ranks that live as threads of ONE process (``ThreadComm``): the engine then needs no CUDA IPC --
     peers' tiles are plain pointers of the same address space.  Used to drive several rank engines on a single GPU
-    (the multi-rank tests on a one-GPU box) and usable for one process driving all GPUs of a box."""
+    (the multi-rank tests on a one-GPU box) and usable for one process driving all GPUs of a box.
+
+    Every rank engine uses up to four CUDA streams and its device-side barriers spin until the peers arrive: the process
+    must start with ``CUDA_DEVICE_MAX_CONNECTIONS`` >= 4 x ranks (default 8, maximum 32), otherwise streams of different
+    ranks share a hardware queue and a kernel queued behind a peer's spinning barrier never starts."""
 
     def __init__(self, n: int, devices=None):
         import threading

@@ -1,6 +1,11 @@
 import os
 import sys
 
+# The rank-thread tests drive several rank engines (4 streams each) inside this one process.  CUDA maps the streams of a
+# process onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that share a queue serialise, and a kernel
+# queued behind another rank's spinning barrier kernel never starts.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
