@@ -80,11 +80,12 @@ def _worker(rank, world, port, case, exchange, q):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs at least 2 GPUs (the same engine runs on one GPU in test_gpu_ranks_one_gpu.py)")
-@pytest.mark.parametrize("exchange", ["fused", "fused+side", "fused+side+graph", "p2p", "p2p+overlap", "p2p+overlap2", "p2p-direct", "nccl"])
-@pytest.mark.parametrize("case", ["L2k128", "L3k16", "L3stale_k6", "banded_k8"])
+@pytest.mark.parametrize("case,exchange",
+                         [("L2k128", e) for e in ("fused", "fused+side", "fused+side+graph", "p2p", "p2p+overlap", "p2p+overlap2",
+                                                  "p2p-direct", "nccl")] +
+                         [("L3k16", "fused+side+graph"), ("L3k16", "p2p+overlap"), ("L3stale_k6", "fused"), ("L3stale_k6", "nccl"),
+                          ("L3stale_k6", "p2p-direct"), ("banded_k8", "fused+side"), ("banded_k8", "p2p"), ("banded_k8", "p2p+overlap2")])
 def test_sharded_engine_on_gpus(case, exchange):
-    if case.startswith("banded") and exchange == "nccl":
-        pytest.skip("the NCCL backend covers the block-diagonal layout only")
     import torch.multiprocessing as mp
     world = min(_n_gpus(), 4)
     ctx = mp.get_context("spawn")
