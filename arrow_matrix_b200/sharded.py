@@ -362,51 +362,79 @@ class FusedPlan:
         self.push_off = push_off
         assert self.push_src.size == 0 or self.push_src.min() >= 0
         # ---- backward: staging slots of every level that receives --------------------------------------------
+        # A staging tile is laid out by SOURCE: [reduced head rows (delivered by GPU 0's reduction) | rows computed by GPU 0 |
+        # GPU 1 | ...], each group in ascending row order of the sending level.  A GPU therefore writes the rows it owes a
+        # peer into one contiguous block of a local send tile (straight from the SpMM epilogue: local stores) and ships the
+        # block with one copy-engine transfer; rows that stay on the GPU go straight into its own staging tile.  (Measured
+        # on 2 B200: storing the rows into the peer's memory from the epilogue instead ran the level-1 SpMM at 3.7 ms against
+        # 0.75 ms with local stores -- NVLink stores trickling out of a latency-bound kernel reach 170 GB/s.)
         self.stage_rows = [0] * max(L - 1, 0)                              # my staging tile of level j (filled by level j+1)
+        self.send_rows = [0] * L                                           # my send tile of level j >= 1
+        self.send_plan: List[list] = [[] for _ in range(L)]                # level j: (dest, send_off, rows, dest_stage_off)
         self.add_map: List[Optional[np.ndarray]] = [None] * L              # local row of level j -> slot in my staging tile
-        self.out_which: List[Optional[np.ndarray]] = [None] * L            # level j >= 1: 0 = local C tile, 1+d = staging tile of d
+        self.out_which: List[Optional[np.ndarray]] = [None] * L            # level j >= 1: 0 = local C tile, 1 = my staging tile, 2 = my send tile
         self.out_row: List[Optional[np.ndarray]] = [None] * L
-        self.head_which: List[Optional[np.ndarray]] = [None] * L           # GPU 0 only: where the reduced head rows go
+        self.head_which: List[Optional[np.ndarray]] = [None] * L           # GPU 0 only: reduced head rows: 1 + d = staging tile of GPU d
         self.head_row: List[Optional[np.ndarray]] = [None] * L
         for j in range(1, L):
             rows_j, rows_p = pl.levels[j].rows_global, pl.levels[j - 1].rows_global
-            bp = pl.levels[j - 1].bounds
-            tn = pl.to_next[j - 1][:rows_p]
-            receives = tn < rows_j                                         # rows of level j-1 that get a contribution
-            before = np.concatenate([[0], np.cumsum(receives)]).astype(np.int64)
+            bp, bj = pl.levels[j - 1].bounds, pl.levels[j].bounds
+            hr = min(w, rows_j)
+            tp = pl.to_prev[j][:rows_j]
+            gs = np.flatnonzero(tp < rows_p)                               # routed rows of level j, ascending
+            dest = np.searchsorted(bp, tp[gs], side="right") - 1           # GPU that owns the receiving row
+            group = np.where(gs < hr, 0, 1 + (np.searchsorted(bj, gs, side="right") - 1))
+            order = np.lexsort((gs, group, dest))                          # slot order inside every destination
+            d_sorted, g_sorted, grp_sorted = dest[order], gs[order], group[order]
+            d_start = np.searchsorted(d_sorted, np.arange(world + 1), side="left")
+            slot = np.arange(order.size, dtype=np.int64) - d_start[d_sorted]
+            slot_of = np.full(rows_j, -1, dtype=np.int64)                  # level-j row -> slot at its destination
+            slot_of[g_sorted] = slot
+            dest_of = np.full(rows_j, -1, dtype=np.int64)
+            dest_of[g_sorted] = d_sorted
+            self.stage_rows[j - 1] = int(d_start[me + 1] - d_start[me])
+            # receiving side: own row of level j-1 -> slot
             shp = pl.levels[j - 1]
-            self.stage_rows[j - 1] = int(before[shp.r1] - before[shp.r0])
             am = np.full(shp.local_rows, -1, dtype=np.int64)
             own = np.arange(shp.r0, shp.r1, dtype=np.int64)
-            am[shp.hoff:shp.hoff + own.size] = np.where(receives[own], before[own] - before[shp.r0], -1)
+            tn = pl.to_next[j - 1][own]
+            has = tn < rows_j
+            am[shp.hoff:shp.hoff + own.size] = np.where(has, slot_of[np.where(has, tn, 0)], -1)
             self.add_map[j - 1] = am
-
-            def route(g):
-                """(which, row) of level-j rows ``g``: the staging slot at the owner of to_prev_j[g]"""
-                tp = pl.to_prev[j][g]
-                valid = tp < rows_p
-                tps = np.where(valid, tp, 0)
-                dst = np.searchsorted(bp, tps, side="right") - 1
-                return np.where(valid, 1 + dst, -1).astype(np.int32), np.where(valid, before[tps] - before[bp[dst]], 0)
-
+            # sending side: my own rows of level j
             sh = pl.levels[j]
             which = np.full(sh.local_rows, -1, dtype=np.int32)
             row = np.zeros(sh.local_rows, dtype=np.int64)
-            hr = min(w, rows_j)
             if me > 0:                                                     # partial head rows stay local (reduced by GPU 0)
                 which[:hr] = 0
                 row[:hr] = np.arange(hr)
             g = np.arange(sh.r0, sh.r1, dtype=np.int64)
             if g.size:
-                wq, rq = route(g)
+                d_g, s_g = dest_of[g], slot_of[g]
                 part = g < hr                                              # GPU 0's own share of block-row 0: a partial sum too
-                wq = np.where(part, 0, wq)
-                rq = np.where(part, sh.hoff + (g - sh.r0), rq)
+                remote = (~part) & (d_g >= 0) & (d_g != me)
+                # send tile: blocks per destination (ascending), rows in ascending g inside a block = the destination's order
+                r_idx = np.flatnonzero(remote)
+                r_order = r_idx[np.argsort(d_g[r_idx], kind="stable")]
+                send_pos = np.full(g.size, -1, dtype=np.int64)
+                send_pos[r_order] = np.arange(r_order.size, dtype=np.int64)
+                self.send_rows[j] = int(r_order.size)
+                cnt = np.bincount(d_g[r_order], minlength=world) if r_order.size else np.zeros(world, dtype=np.int64)
+                off = np.concatenate([[0], np.cumsum(cnt)])
+                for d in range(world):
+                    if cnt[d] > 0:
+                        first = r_order[off[d]]                            # my first row for d: its slot starts my block there
+                        self.send_plan[j].append((d, int(off[d]), int(cnt[d]), int(s_g[first])))
+                        assert np.array_equal(s_g[r_order[off[d]:off[d + 1]]], s_g[first] + np.arange(cnt[d]))
+                wq = np.where(part, 0, np.where(d_g < 0, -1, np.where(d_g == me, 1, 2))).astype(np.int32)
+                rq = np.where(part, sh.hoff + (g - sh.r0), np.where(d_g == me, s_g, send_pos))
                 which[sh.hoff:sh.hoff + g.size] = wq
-                row[sh.hoff:sh.hoff + g.size] = rq
+                row[sh.hoff:sh.hoff + g.size] = np.where(wq >= 0, rq, 0)
             self.out_which[j], self.out_row[j] = which, row
             if me == 0:
-                self.head_which[j], self.head_row[j] = route(np.arange(hr, dtype=np.int64))
+                hg = np.arange(hr, dtype=np.int64)
+                self.head_which[j] = np.where(dest_of[hg] >= 0, 1 + dest_of[hg], -1).astype(np.int32)
+                self.head_row[j] = np.where(dest_of[hg] >= 0, slot_of[hg], 0)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -476,10 +504,14 @@ class ShardedArrowEngine:
             self._recv = (len(rows_per_level), 0)
             rows_per_level.append(max(self.fp.recv_rows, 1))
             tiles_per_level.append(1)
-            self._stg = []
+            self._stg, self._snd = [], [None]
             for j in range(self.L - 1):
                 self._stg.append((len(rows_per_level), 0))
                 rows_per_level.append(max(self.fp.stage_rows[j], 1))
+                tiles_per_level.append(1)
+            for j in range(1, self.L):
+                self._snd.append((len(rows_per_level), 0))
+                rows_per_level.append(max(self.fp.send_rows[j], 1))
                 tiles_per_level.append(1)
         self.tiles = be.alloc_shared_tiles(rows_per_level, self.k, tiles_per_level=tiles_per_level)
         if self.fp is not None:
@@ -715,20 +747,18 @@ class ShardedArrowEngine:
     def _setup_fused(self):
         be, pl, fp = self.be, self.plan, self.fp
         n_cols = fp.x_split + max(fp.recv_rows, 1)
-        self.f_mats, self.f_tables, self.f_tables_dry, self.f_head_tables, self.f_add = [None] * self.L, [None] * self.L, \
-            [None] * self.L, [None] * self.L, [None] * self.L
+        self.f_mats, self.f_tables, self.f_head_tables, self.f_add = [None] * self.L, [None] * self.L, [None] * self.L, [None] * self.L
+        me = self.rank
         for j in range(1, self.L):
-            sh = pl.levels[j]
             if self.mats[j] is not None:
                 self.f_mats[j] = be.fused_matrix(self.mats[j], fp.colmap[j], n_cols)
-            self.f_tables[j] = be.out_table(local=(j, 0), stage=self._stg[j - 1], which=fp.out_which[j], row=fp.out_row[j])
-            # measurement twin: every routed row lands in the local tile instead of a peer's staging slot
-            wd = np.where(fp.out_which[j] >= 0, 0, -1).astype(np.int32)
-            self.f_tables_dry[j] = be.out_table(local=(j, 0), stage=self._stg[j - 1], which=wd,
-                                                row=np.arange(sh.local_rows, dtype=np.int64))
-            if self.rank == 0:
-                self.f_head_tables[j] = be.out_table(local=(j, 0), stage=self._stg[j - 1], which=fp.head_which[j],
-                                                     row=fp.head_row[j])
+            # every SpMM store is local: the level's own tile (partial head rows), my staging tile, my send tile
+            self.f_tables[j] = be.out_table([(me,) + (j, 0), (me,) + self._stg[j - 1], (me,) + self._snd[j]],
+                                            fp.out_which[j], fp.out_row[j])
+            if me == 0:
+                # the reduced head rows are few (one block-row): GPU 0 stores them straight into the owners' staging tiles
+                self.f_head_tables[j] = be.out_table([(me,) + (j, 0)] + [(g,) + self._stg[j - 1] for g in range(self.world)],
+                                                     fp.head_which[j], fp.head_row[j])
         for j in range(self.L - 1):
             n = pl.levels[j].own_rows if j == 0 else pl.levels[j].local_rows
             am = fp.add_map[j][pl.levels[j].hoff:pl.levels[j].hoff + n] if j == 0 else fp.add_map[j]
@@ -738,9 +768,9 @@ class ShardedArrowEngine:
 
     def _step_fused(self, dry: bool = False):
         """forward push || level-0 SpMM ; deepest level first: SpMM with the [tile | receive region] operand, rows written
-        into the owners' staging tiles ; head reductions ; one final gather-add.  ``dry``: the same launches with every
-        cross-GPU effect removed (no push, no barriers, local pointer tables) -- the time this step would take if
-        communication were free; bench.py reports the difference as exposed communication."""
+        into my staging / send tiles, one copy-engine transfer per peer ; head reductions ; one final gather-add.  ``dry``: the
+        same kernels with every cross-GPU effect removed (no push, no copies, no barriers, no head reductions) -- the time this
+        step would take if communication were free; bench.py reports the difference as exposed communication."""
         be, pl = self.be, self.plan
         side = self.overlap
         L = self.L
@@ -760,10 +790,11 @@ class ShardedArrowEngine:
             be.limit_spmm(self.side_ctas)
         for j in range(L - 1, 0, -1):
             if self.f_mats[j] is not None and pl.levels[j].local_rows > 0:
-                be.spmm_fused(self.f_mats[j], x, self._recv, self.fp.x_split,
-                              self.f_tables_dry[j] if dry else self.f_tables[j],
+                be.spmm_fused(self.f_mats[j], x, self._recv, self.fp.x_split, self.f_tables[j],
                               add=self._stg[j] if j < L - 1 else None, add_map=self.f_add[j] if j < L - 1 else None, side=side)
             if not dry:
+                for d, src_off, rows, dst_off in self.fp.send_plan[j]:      # backward exchange: one contiguous block per peer
+                    be.copy_to_peer(d, self._stg[j - 1], dst_off, self._snd[j], src_off, rows, side=side)
                 be.barrier(side)                                # partial head rows written, routed rows delivered
                 if self.rank == 0:
                     be.reduce_rows((j, 0), hr[j], table=self.f_head_tables[j], side=side)
@@ -1177,10 +1208,17 @@ class CudaPeerBackend:
     def fused_matrix(self, A, colmap, n_cols):
         return A.remap_columns(self.ctx.map_upload(colmap, n_cols), n_cols)
 
-    def out_table(self, local, stage, which, row):
-        """pointer table over [my tile ``local``] + [staging tile ``stage`` of every rank]"""
-        tiles = [self._peer[self.rank][local[0]][local[1]]] + [self._peer[g][stage[0]][stage[1]] for g in range(self.world)]
-        return self.ctx.ptrtable_upload(tiles, which, row)
+    def out_table(self, tiles, which, row):
+        """pointer table over ``tiles`` = [(rank, level, index), ...]"""
+        return self.ctx.ptrtable_upload([self._peer[g][lv][ix] for g, lv, ix in tiles], which, row)
+
+    def copy_to_peer(self, peer, dst, dst_off, src, src_off, rows, side=False):
+        """rows [src_off, src_off+rows) of my tile ``src`` -> rows [dst_off, ...) of ``peer``'s tile ``dst`` (copy engine)"""
+        self._lane(side)
+        try:
+            self._view(peer, dst[0], dst[1], dst_off, rows).copy_from(self._view(self.rank, src[0], src[1], src_off, rows), rows=rows)
+        finally:
+            self._lane(False)
 
     def push_plan(self, recv, src_rows, bounds, offs, src_limit):
         m = self.ctx.map_upload(src_rows, max(int(src_limit), 1))

@@ -61,10 +61,10 @@ def main():
             eng.close()
             continue
         configs = []
-        for graphs in (1, 0):
-            for ov, mc, sc in ((1, 2, 2), (1, 3, 1), (1, 1, 3), (1, 3, 2), (1, 2, 3), (1, 4, 4), (0, 0, 0)):
-                configs.append((graphs, ov, mc, sc, 0))
-        for pc in (32, 74, 148, 592):
+        for ov, mc, sc in ((1, 2, 2), (1, 3, 1), (1, 1, 3), (1, 3, 2), (1, 2, 3), (1, 4, 4), (0, 0, 0)):
+            configs.append((1, ov, mc, sc, 0))
+        configs.append((0, 1, 2, 2, 0))
+        for pc in (74, 148):
             configs.append((1, 1, 2, 2, pc))
         for graphs, ov, mc, sc, pc in configs:
             eng.overlap = bool(ov)
@@ -104,8 +104,12 @@ def main():
                   "final_add": t(lambda: be.final_add((0, x[1] ^ 1), eng.plan.levels[0].hoff, eng.plan.levels[0].own_rows, eng._stg[0], eng.f_add[0]))}
         for j in range(1, L):
             if eng.f_mats[j] is not None:
-                phases[f"l{j}_spmm_push"] = t(lambda j=j: be.spmm_fused(eng.f_mats[j], x, eng._recv, eng.fp.x_split, eng.f_tables[j]))
-                phases[f"l{j}_spmm_local"] = t(lambda j=j: be.spmm_fused(eng.f_mats[j], x, eng._recv, eng.fp.x_split, eng.f_tables_dry[j]))
+                phases[f"l{j}_spmm"] = t(lambda j=j: be.spmm_fused(eng.f_mats[j], x, eng._recv, eng.fp.x_split, eng.f_tables[j]))
+
+            def copies(j=j):
+                for d, src_off, rows, dst_off in eng.fp.send_plan[j]:
+                    be.copy_to_peer(d, eng._stg[j - 1], dst_off, eng._snd[j], src_off, rows)
+            phases[f"l{j}_copies"] = t(copies)
         fp = eng.fp
         out({"n": world, "k": a.k, "phases_ms": {kk: round(v, 4) for kk, v in phases.items()},
              "recv_rows_rank0": int(fp.recv_rows), "push_rows_rank0": int(fp.push_bounds[-1]), "stage_rows_rank0": fp.stage_rows,

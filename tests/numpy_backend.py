@@ -84,22 +84,25 @@ class GlooNumpyBackend:
         assert np.all(idx >= 0) and np.all(idx < n_cols)
         return sparse.csr_matrix((A.data, idx, A.indptr), shape=(A.shape[0], n_cols), dtype=np.float32)
 
-    def out_table(self, local, stage, which, row):
-        return dict(local=local, stage=stage, which=np.asarray(which), row=np.asarray(row, dtype=np.int64))
+    def out_table(self, tiles, which, row):
+        return dict(tiles=list(tiles), which=np.asarray(which), row=np.asarray(row, dtype=np.int64))
 
     def _store(self, table, values):
         """rows of ``values`` to wherever the table routes them"""
         which, row = table["which"], table["row"]
-        sel = np.flatnonzero(which[: values.shape[0]] == 0)
-        self.tiles[table["local"][0]][table["local"][1]][row[sel]] = values[sel]
-        for d in range(self.world):
-            sel = np.flatnonzero(which[: values.shape[0]] == 1 + d)
+        for t, (g, lv, ix) in enumerate(table["tiles"]):
+            sel = np.flatnonzero(which[: values.shape[0]] == t)
             if sel.size == 0:
                 continue
-            if d == self.rank:
-                self.tiles[table["stage"][0]][table["stage"][1]][row[sel]] = values[sel]
+            if g == self.rank:
+                self.tiles[lv][ix][row[sel]] = values[sel]
             else:
-                self.__dict__.setdefault("outbox", []).append((d, table["stage"][0], table["stage"][1], row[sel].copy(), values[sel].copy()))
+                self.__dict__.setdefault("outbox", []).append((g, lv, ix, row[sel].copy(), values[sel].copy()))
+
+    def copy_to_peer(self, peer, dst, dst_off, src, src_off, rows, side=False):
+        assert peer != self.rank
+        data = self.tiles[src[0]][src[1]][src_off:src_off + rows].copy()
+        self.__dict__.setdefault("outbox", []).append((peer, dst[0], dst[1], dst_off + np.arange(rows, dtype=np.int64), data))
 
     def push_plan(self, recv, src_rows, bounds, offs, src_limit):
         return dict(recv=recv, src=np.asarray(src_rows, dtype=np.int64), bounds=[int(b) for b in bounds], offs=[int(o) for o in offs])
