@@ -431,9 +431,12 @@ def run_b200(a):
     tag = f"ba_{a.vertices}_{a.ba_m}" if a.workload == "ba" else f"{a.blocks}_{a.perm}"
     base = os.path.join(ROOT, "tmp", f"bench_{tag}_{a.width}_{a.levels}")
     if rank == 0:
-        dec0 = build_decomposition(a)
-        graphio.save_decomposition_new(dec0, base, a.width, block_diagonal=True)
-        del dec0
+        done = base + ".complete"                           # written last: an interrupted generation is redone
+        if not os.path.exists(done):
+            dec0 = build_decomposition(a)
+            graphio.save_decomposition_new(dec0, base, a.width, block_diagonal=True)
+            del dec0
+            open(done, "w").close()
     comm.Barrier()
     arrow, eng, blocks = build_engine(a, comm, base, a.k, local_rank)
     dec = blocks.decomposition                 # memory-mapped level files (for the full-size property check)

@@ -107,9 +107,9 @@ def main():
                 phases[f"l{j}_spmm"] = t(lambda j=j: be.spmm_fused(eng.f_mats[j], x, eng._recv, eng.fp.x_split, eng.f_tables[j]))
 
             def copies(j=j):
-                for d, src_off, rows, dst_off in eng.fp.send_plan[j]:
-                    be.copy_to_peer(d, eng._stg[j - 1], dst_off, eng._snd[j], src_off, rows)
-            phases[f"l{j}_copies"] = t(copies)
+                for sr, src_off, rows, dst_off in eng.fp.recv_plan[j]:
+                    be.copy_rows_from_peer(dst=eng._stg[j - 1], dst_off=dst_off, peer=sr, src=eng._snd[j], src_off=src_off, rows=rows)
+            phases[f"l{j}_pulls"] = t(copies)
         fp = eng.fp
         out({"n": world, "k": a.k, "phases_ms": {kk: round(v, 4) for kk, v in phases.items()},
              "recv_rows_rank0": int(fp.recv_rows), "push_rows_rank0": int(fp.push_bounds[-1]), "stage_rows_rank0": fp.stage_rows,

@@ -198,7 +198,7 @@ class GlooNumpyBackend:
             else:
                 d[dst_off + sel] = rows
 
-    def copy_rows_from_peer(self, dst, dst_off, peer, src, src_off, rows):
+    def copy_rows_from_peer(self, dst, dst_off, peer, src, src_off, rows, side=False):
         self.tiles[dst[0]][dst[1]][dst_off:dst_off + rows] = self._tile(peer, src[0], src[1])[src_off:src_off + rows]
 
     def bcast_head(self, tile, rows):
