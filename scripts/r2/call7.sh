@@ -2,7 +2,7 @@
 # round 2, GPU call 7 (8 GPUs): parity at 4 ranks, schedule sweep at 8, bench lines at 8 / 4 / 2
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/c7_topo.txt 2>&1
-timeout 400 python -m pytest tests/test_gpu_multi.py -x -q --tb=short -p no:cacheprovider -k "L2k128-fused+side+graph or L3k16-fused or banded_k8-fused or L3stale_k6-fused" 2>&1 | tail -3 | tee gpurun_out/c7_pytest.log
+timeout 400 python -m pytest tests/test_gpu_multi.py -x -q --tb=short -p no:cacheprovider -k "fused" 2>&1 | tail -3 | tee gpurun_out/c7_pytest.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 \
     scripts/r2/mg_sweep.py --gpus 8 --k 128 --steps 20 2>gpurun_out/c7_sweep_n8_k128.err | grep "^{" | tee gpurun_out/c7_sweep_n8_k128.jsonl | cut -c1-330
 for N in 8 4 2; do
