@@ -104,17 +104,17 @@ class GlooNumpyBackend:
         data = self.tiles[src[0]][src[1]][src_off:src_off + rows].copy()
         self.__dict__.setdefault("outbox", []).append((peer, dst[0], dst[1], dst_off + np.arange(rows, dtype=np.int64), data))
 
-    def push_plan(self, recv, src_rows, bounds, offs, src_limit):
-        return dict(recv=recv, src=np.asarray(src_rows, dtype=np.int64), bounds=[int(b) for b in bounds], offs=[int(o) for o in offs])
+    def push_plan(self, recv, src_rows, bounds, offs, dests, src_limit):
+        return dict(recv=recv, src=np.asarray(src_rows, dtype=np.int64), bounds=[int(b) for b in bounds], offs=[int(o) for o in offs],
+                    dests=[int(d) for d in dests])
 
     def push(self, pp, x, side=False):
         X = self.tiles[x[0]][x[1]]
-        for d in range(self.world):
-            a, b = pp["bounds"][d], pp["bounds"][d + 1]
-            if b > a:
-                assert d != self.rank
-                rows = pp["offs"][d] + np.arange(b - a, dtype=np.int64)
-                self.__dict__.setdefault("outbox", []).append((d, pp["recv"][0], pp["recv"][1], rows, X[pp["src"][a:b]].copy()))
+        for i, d in enumerate(pp["dests"]):
+            a, b = pp["bounds"][i], pp["bounds"][i + 1]
+            assert d != self.rank and b > a
+            rows = pp["offs"][i] + np.arange(b - a, dtype=np.int64)
+            self.__dict__.setdefault("outbox", []).append((d, pp["recv"][0], pp["recv"][1], rows, X[pp["src"][a:b]].copy()))
 
     def spmm_fused(self, A, x, recv, x_split, table, add=None, add_map=None, side=False):
         Xc = np.concatenate([self.tiles[x[0]][x[1]][:x_split], self.tiles[recv[0]][recv[1]]])
