@@ -227,7 +227,7 @@ class Context:
 
     OPT_L2_HINTS_PLAIN, OPT_L2_HINTS_FUSED, OPT_BIG_TILES, OPT_SPMM_CTAS_PER_SM, OPT_PREFETCH = 1, 2, 3, 4, 5
     OPT_ROWS_PER_GROUP, OPT_SPMM_SM_LIMIT, OPT_PUSH_CTAS, OPT_BARRIER_TIMEOUT_MS, OPT_SMEM_CARVEOUT = 6, 7, 8, 9, 10
-    OPT_FORCE_PREDICATED, OPT_TILE_KERNEL = 11, 12
+    OPT_FORCE_PREDICATED, OPT_TILE_KERNEL, OPT_PUSH_INTERLEAVE = 11, 12, 13
 
     def set_option(self, option: int, value: int):
         self._check(self.lib.arrow_set_option(self._h, int(option), int(value)))

@@ -432,7 +432,7 @@ class FusedPlan:
                 self.send_rows[j] = int(r_order.size)
                 cnt = np.bincount(d_g[r_order], minlength=world) if r_order.size else np.zeros(world, dtype=np.int64)
                 off = np.concatenate([[0], np.cumsum(cnt)])
-                for d in range(world):
+                for d in ((me + t) % world for t in range(1, world)):      # rotated like the forward push
                     if cnt[d] > 0:
                         first = r_order[off[d]]                            # my first row for d: its slot starts my block there
                         self.send_plan[j].append((d, int(off[d]), int(cnt[d]), int(s_g[first])))
@@ -775,6 +775,15 @@ class ShardedArrowEngine:
             am = fp.add_map[j][pl.levels[j].hoff:pl.levels[j].hoff + n] if j == 0 else fp.add_map[j]
             self.f_add[j] = be.map_upload(am, max(fp.stage_rows[j], 1))
         self.f_push = be.push_plan(self._recv, fp.push_src, fp.push_bounds, fp.push_off, fp.push_dest, pl.levels[0].local_rows)
+        # backward exchange, variant "push": the same kernel ships the blocks of my send tile into the peers' staging tiles
+        self.f_bpush = [None] * self.L
+        for j in range(1, self.L):
+            plan_j = fp.send_plan[j]
+            src = np.concatenate([np.arange(o, o + r, dtype=np.int64) for _, o, r, _ in plan_j]) if plan_j else np.zeros(0, dtype=np.int64)
+            bounds = np.concatenate([[0], np.cumsum([r for _, _, r, _ in plan_j])]).astype(np.int64)
+            self.f_bpush[j] = be.push_plan(self._stg[j - 1], src, bounds, [so for _, _, _, so in plan_j], [d for d, _, _, _ in plan_j],
+                                           max(fp.send_rows[j], 1))
+        self.bwd_mode = "push"           # "push": SM kernel, all peers at once | "pull": one copy-engine transfer per peer
         self.side_ctas, self.main_ctas = 2, 2
 
     def _step_fused(self, dry: bool = False):
@@ -804,12 +813,14 @@ class ShardedArrowEngine:
                 be.spmm_fused(self.f_mats[j], x, self._recv, self.fp.x_split, self.f_tables[j],
                               add=self._stg[j] if j < L - 1 else None, add_map=self.f_add[j] if j < L - 1 else None, side=side)
             if not dry:
-                be.barrier(side)                                # every peer's send tile and partial head rows are written
-                # backward exchange: one contiguous block per peer, PULLED by the copy engine (2 B200: 746 GB/s pulled,
-                # 510 GB/s when the sender pushes the same block)
-                for src_rank, src_off, rows, dst_off in self.fp.recv_plan[j]:
-                    be.copy_rows_from_peer(dst=self._stg[j - 1], dst_off=dst_off, peer=src_rank, src=self._snd[j], src_off=src_off,
-                                           rows=rows, side=side)
+                if self.bwd_mode == "push":
+                    be.push(self.f_bpush[j], self._snd[j], side=side)   # my blocks into the peers' staging tiles, all peers at once
+                be.barrier(side)                                # every peer's send tile / pushed block and partial head rows are written
+                if self.bwd_mode != "push":
+                    # one contiguous block per peer, pulled by the copy engine (no SM time; one source at a time)
+                    for src_rank, src_off, rows, dst_off in self.fp.recv_plan[j]:
+                        be.copy_rows_from_peer(dst=self._stg[j - 1], dst_off=dst_off, peer=src_rank, src=self._snd[j], src_off=src_off,
+                                               rows=rows, side=side)
                 if self.rank == 0:
                     be.reduce_rows((j, 0), hr[j], table=self.f_head_tables[j], side=side)
                 be.barrier(side)                                # the reduced head rows have landed; send tiles may be rewritten

@@ -83,6 +83,8 @@ int  arrow_set_tuning(arrow_ctx *ctx, int long_row_threshold, int long_row_segme
 #define ARROW_OPT_FORCE_PREDICATED 11  /* 1: the tile kernel takes its predicated gather path even when every column is valid (measurement switch) */
 #define ARROW_OPT_TILE_KERNEL     12   /* 1 (default): plain / row-map / accumulate launches with one row per lane group run the round-1 tile
                                         kernel, 0: the generalised kernel everywhere (A/B switch, profiles/r02_kernel_sweep.md) */
+#define ARROW_OPT_PUSH_INTERLEAVE 13   /* 1 (default): arrow_push_rows walks its destination blocks interleaved (every peer is written to at
+                                        every instant); 0: block after block */
 #define ARROW_OPT_BARRIER_TIMEOUT_MS 9 /* arrow_peer_barrier gives up after this long (default 30000) and poisons the context */
 int  arrow_set_option(arrow_ctx *ctx, int option, int value);
 

@@ -39,7 +39,8 @@ def main():
         if rank == 0:
             print(json.dumps(d), flush=True)
 
-    for mode in ("auto", "exchange"):
+    lean = os.environ.get("SWEEP_LEAN") == "1"
+    for mode in (("auto",) if lean else ("auto", "exchange")):
         a.mode = mode
         arrow, eng, blocks = bench.build_engine(a, comm, base, a.k, local_rank)
         ctx = eng.ctx
@@ -66,6 +67,17 @@ def main():
         configs.append((0, 1, 2, 2, 0))
         for pc in (74, 148):
             configs.append((1, 1, 2, 2, pc))
+        if lean:
+            configs = [(1, 1, 2, 2, 0), (1, 1, 3, 2, 0), (1, 0, 0, 0, 0)]
+        for bwd, il in (("push", 1), ("pull", 1), ("pull", 0), ("push", 0)):
+            eng.bwd_mode = bwd
+            ctx.set_option(ctx.OPT_PUSH_INTERLEAVE, il)
+            eng.overlap, eng.main_ctas, eng.side_ctas, eng.use_graphs = True, 2, 2, True
+            eng.graphs, eng._graph_warm = {}, set()
+            ms = mx(bench.time_steps(eng, ctx, barrier, a.steps, 4))
+            out({"n": world, "k": a.k, "mode": eng.mode, "bwd_mode": bwd, "push_interleave": il, "ms_per_step": round(ms, 4)})
+        eng.bwd_mode = "push"
+        ctx.set_option(ctx.OPT_PUSH_INTERLEAVE, 1)
         for graphs, ov, mc, sc, pc in configs:
             eng.overlap = bool(ov)
             eng.main_ctas, eng.side_ctas = mc, sc
@@ -110,6 +122,7 @@ def main():
                 for sr, src_off, rows, dst_off in eng.fp.recv_plan[j]:
                     be.copy_rows_from_peer(dst=eng._stg[j - 1], dst_off=dst_off, peer=sr, src=eng._snd[j], src_off=src_off, rows=rows)
             phases[f"l{j}_pulls"] = t(copies)
+            phases[f"l{j}_bpush"] = t(lambda j=j: be.push(eng.f_bpush[j], eng._snd[j]))
         fp = eng.fp
         out({"n": world, "k": a.k, "phases_ms": {kk: round(v, 4) for kk, v in phases.items()},
              "recv_rows_rank0": int(fp.recv_rows), "push_rows_rank0": int(fp.push_bounds[-1]), "stage_rows_rank0": fp.stage_rows,

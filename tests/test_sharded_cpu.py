@@ -86,6 +86,8 @@ def _run_case(rank, world, case, overlap):
     fused = isinstance(overlap, str)            # "fused" / "fused-side": the fused step (serial / side-lane schedule)
     if fused:
         eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=(overlap == "fused-side"), mode="auto")
+        if eng.fp is not None and overlap == "fused-side":
+            eng.bwd_mode = "pull"               # both backward transports: SM push (default) and copy-engine pulls
         # rows behind the sentinel only force the literal protocol when some non-zero READS one of them (then the
         # engine must have fallen back on its own); either way the numbers below have to match the oracle
         if case == "L3stale":
