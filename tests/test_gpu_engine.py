@@ -221,3 +221,59 @@ def test_ones_step_property_at_benchmark_scale(cuda_device):
     eng.close()
     assert v.get("ok") is True, v
     assert v["rows"] == blocks * w and v["max_rel_err"] <= 1e-5
+
+
+# ---- BASELINE.json configurations with real values (round 2) --------------------------------------
+def test_baseline_config1_100k_rows_k16_two_levels_chained(cuda_device, tmp_path):
+    """BASELINE.json configs[0]: random 100k-row, width 10 000, k = 16 decomposition, through the level files and the public
+    classes, three chained iterations like the reference's own test (tests/test_arrowmpi.py:164-166), against the oracle"""
+    from arrow_matrix_b200 import graphio
+    from arrow_matrix_b200.arrow_dec_mpi import ArrowDecompositionMPI
+    from arrow_matrix_b200.comm import SelfComm
+    w, t0, k = 10000, 10, 16
+    dec = synth.synth_decomposition(t0, w, levels=2, perm_kind="random", seed=503)
+    base = str(tmp_path / "cfg1")
+    graphio.save_decomposition_new(dec, base, w, block_diagonal=True)
+    comm = SelfComm()
+    blocks, n_blocks, to_prev, to_next = ArrowDecompositionMPI.load_decomposition_new(comm, base, w, True, slim=True)
+    arrow = ArrowDecompositionMPI.initialize(comm, n_blocks, to_prev, to_next, w, k, 'gpu', True, True)
+    arrow.B.load_sparse_matrix_from_blocks(blocks)
+    arrow.B.zero_rhs(w, k)
+    po = oracle.ReferenceProtocolOracle(dec, w, k, use_c_kernel=True)
+    po64 = oracle.ReferenceProtocolOracle(dec, w, k, dtype=np.float64)
+    X = synth.generate_dense_matrix(t0 * w, k, np.float32, np.random.default_rng(42))
+    arrow.B.set_features(X)
+    po.set_features(X.copy())
+    po64.set_features(X)
+    for it in range(3):
+        arrow.step()
+        ref = po.step()
+        got = arrow.B.result_tile()
+        assert_close(got, ref, exact=po64.step())
+        po.C[0][:] = got                                   # compare every product from the same starting point
+        po64.C[0][:] = got
+    arrow._engine.close()
+
+
+@pytest.mark.parametrize("recipe", ["uniform", "arrow"])
+def test_baseline_configs_2_3_one_million_row_block_k_sweep(cuda_device, recipe):
+    """BASELINE.json configs[1] and [2]: one 1M x 1M CSR with ~10 non-zeros per row times dense k in {16, 32, 64, 128, 256},
+    fp32 -- the reference's generator recipe (uniform columns, arrow/common/utils.py:63-87, rng 42) and the arrow-structured
+    variant of SURVEY 8d -- against the restated SciPy kernel (oracle/csr_matvecs.c), 1e-5 of the largest entry"""
+    n = 1_000_000
+    rng = np.random.default_rng(42)
+    A = synth.generate_sparse_matrix(n, n, 10 * n, np.float32, rng) if recipe == "uniform" else synth.arrow_csr(n, 10000, 100, rng)
+    ctx = _lib.Context(cuda_device)
+    dA = ctx.csr_from_scipy(A)
+    for k in (16, 32, 64, 128, 256):
+        X = synth.generate_dense_matrix(n, k, np.float32, rng)
+        dX, dC = ctx.dense_from_host(X), ctx.dense_alloc(n, k)
+        ctx.spmm(dA, dX, dC)
+        got = dC.d2h()
+        ref = oracle.csr_spmm_c(A, X)
+        scale = float(np.max(np.abs(ref)))
+        err = float(np.max(np.abs(got - ref)))
+        assert err <= 1e-5 * scale, (recipe, k, err / scale)
+        dX.free()
+        dC.free()
+    ctx.close()

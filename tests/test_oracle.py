@@ -151,7 +151,10 @@ def test_npy_layout_roundtrip(tmp_path):
     back2 = graphio.load_decomposition_new(base2, 8, True)
     assert np.all(back2[0][0].data == 1.0) and back2[0][0].data.dtype == np.float32
     raw = graphio.load_decomposition_new(base2, 8, True, mem_map=True)
-    assert raw[0][0][0] is None and raw[0][0][1].dtype == np.int64 and raw[0][0][2].dtype == np.int64
+    # value-less files: ones like the reference (graphio.py:292-298), as a zero-stride view on the memory-mapped route
+    ones = raw[0][0][0]
+    assert ones.dtype == np.float32 and ones.shape == raw[0][0][1].shape and ones.strides == (0,) and np.all(ones[:5] == 1.0)
+    assert raw[0][0][1].dtype == np.int64 and raw[0][0][2].dtype == np.int64
     assert back2[0][1].min() == 1
 
 
