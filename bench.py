@@ -231,8 +231,8 @@ def run_reference(a):
 def expected_step_on_vector(decomposition, width, u, block_diagonal=True):
     """float64 result column of ONE step applied to the vector ``u`` (level-0 row order): forward exchange through the
     level maps, every level's arrow blocks, backward scatter-add -- host arithmetic on the CSR arrays only, one sparse
-    mat-vec per level.  Returns ``(y, state_free)``; ``state_free`` is False when some row lies behind the sentinel (its
-    value then depends on earlier iterations, arrow_dec_mpi.py:544) and the property does not apply."""
+    mat-vec per level.  Returns ``(y, state_free)``; ``state_free`` is False when some non-zero reads a row behind the
+    sentinel (that row keeps the previous iteration's value, arrow_dec_mpi.py:544) and the property does not apply."""
     from scipy import sparse
     from arrow_matrix_b200 import decomp
     L = len(decomposition)
@@ -240,15 +240,21 @@ def expected_step_on_vector(decomposition, width, u, block_diagonal=True):
     _, to_prev, _, _ = decomp.prepare_permutations([p for _, p in decomposition], n_blocks, width)
     rows = [int(b) * width for b in n_blocks]
     x = [np.asarray(u, dtype=np.float64)[: rows[0]]]
-    state_free = True
+    fed = [np.ones(rows[0], dtype=bool)]                    # rows whose value this iteration defines (chain down to level 0)
     for j in range(1, L):
         tp = to_prev[j][: rows[j]]
         valid = tp < rows[j - 1]
-        state_free = state_free and bool(valid.all())
-        x.append(np.where(valid, x[j - 1][np.where(valid, tp, 0)], 0.0))
+        safe = np.where(valid, tp, 0)
+        fed.append(valid & fed[j - 1][safe])
+        x.append(np.where(fed[j], x[j - 1][safe], 0.0))
     c = []
+    state_free = True
     for j, (B, _) in enumerate(decomposition):
         ip, idx, dat, _ = decomp.arrow_rows(B, width, n_blocks[j], block_diagonal, 0, rows[j])
+        # a row behind the sentinel keeps the previous iteration's value (arrow_dec_mpi.py:544): it only matters -- and
+        # makes the result depend on history -- if some non-zero READS it (real decompositions have such rows but no reader)
+        if idx.size and not bool(fed[j][idx].all()):
+            state_free = False
         vals = np.ones(idx.size) if dat is None else np.asarray(dat, dtype=np.float64)
         c.append(sparse.csr_matrix((vals, idx, ip), shape=(rows[j], rows[j])) @ x[j])
     for j in range(L - 1, 0, -1):
@@ -478,6 +484,15 @@ def run_b200(a):
 
     # ---- exposed communication (N > 1): the same launches with every cross-GPU effect removed ------------------
     exposed = None
+    if world > 1 and not fused_n:
+        # literal protocol (mode=exchange): compute-only = every level's local SpMM launch, back to back, nothing else
+        def only_spmm():
+            xi, ci = list(eng.xi), list(eng.ci)
+            eng.spmm()
+            eng.xi, eng.ci = xi, ci
+        dry_ms = max_over_ranks(dist, torch, time_steps(eng, ctx, barrier, a.steps, 2, step_fn=only_spmm))
+        exposed = {"exposed_comm_ms": max(ms_step - dry_ms, 0.0), "compute_only_ms": dry_ms,
+                   "how": "step time minus the time of the per-level SpMM launches alone (max over ranks each)"}
     if fused_n and world > 1:
         dry_ms = max_over_ranks(dist, torch, time_steps(eng, ctx, barrier, a.steps, 2, step_fn=lambda: eng._step_fused(dry=True)))
         exposed = {"exposed_comm_ms": max(ms_step - dry_ms, 0.0), "compute_only_ms": dry_ms,
