@@ -1237,14 +1237,6 @@ class CudaPeerBackend:
         """pointer table over ``tiles`` = [(rank, level, index), ...]"""
         return self.ctx.ptrtable_upload([self._peer[g][lv][ix] for g, lv, ix in tiles], which, row)
 
-    def copy_to_peer(self, peer, dst, dst_off, src, src_off, rows, side=False):
-        """rows [src_off, src_off+rows) of my tile ``src`` -> rows [dst_off, ...) of ``peer``'s tile ``dst`` (copy engine)"""
-        self._lane(side)
-        try:
-            self._view(peer, dst[0], dst[1], dst_off, rows).copy_from(self._view(self.rank, src[0], src[1], src_off, rows), rows=rows)
-        finally:
-            self._lane(False)
-
     def push_plan(self, recv, src_rows, bounds, offs, dests, src_limit):
         """block i = rows bounds[i]..bounds[i+1] of ``src_rows`` -> rows offs[i].. of GPU dests[i]'s receive region"""
         m = self.ctx.map_upload(src_rows, max(int(src_limit), 1))

@@ -99,11 +99,6 @@ class GlooNumpyBackend:
             else:
                 self.__dict__.setdefault("outbox", []).append((g, lv, ix, row[sel].copy(), values[sel].copy()))
 
-    def copy_to_peer(self, peer, dst, dst_off, src, src_off, rows, side=False):
-        assert peer != self.rank
-        data = self.tiles[src[0]][src[1]][src_off:src_off + rows].copy()
-        self.__dict__.setdefault("outbox", []).append((peer, dst[0], dst[1], dst_off + np.arange(rows, dtype=np.int64), data))
-
     def push_plan(self, recv, src_rows, bounds, offs, dests, src_limit):
         return dict(recv=recv, src=np.asarray(src_rows, dtype=np.int64), bounds=[int(b) for b in bounds], offs=[int(o) for o in offs],
                     dests=[int(d) for d in dests])

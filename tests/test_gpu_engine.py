@@ -218,9 +218,11 @@ def test_ones_step_property_at_benchmark_scale(cuda_device):
     eng = ArrowEngine(dec, w, k, device=cuda_device)
     hx, hc = _lib.PinnedArray((blocks * w, k)), _lib.PinnedArray((blocks * w, k))
     v = bench.verify_ones_step(eng, dec, w, 0, hx, hc, SelfComm())
+    v1 = bench.verify_rank1_step(eng, dec, w, 0, hx, hc, SelfComm())        # the property the bench line carries since round 2
     eng.close()
     assert v.get("ok") is True, v
     assert v["rows"] == blocks * w and v["max_rel_err"] <= 1e-5
+    assert v1.get("ok") is True and v1["rows"] == blocks * w and v1["max_rel_err"] <= 1e-5, v1
 
 
 # ---- BASELINE.json configurations with real values (round 2) --------------------------------------
