@@ -338,3 +338,65 @@ def test_locality_partition_rules():
     assert b is not None and b[1] >= 1
     # one GPU would get everything: too skewed
     assert decomp.locality_partition(ident % 16, nb, w, prev, parts, max_skew=2.0) is None
+
+
+@pytest.mark.parametrize("world,case", [(8, "L2"), (8, "L3"), (8, "banded"), (5, "L2"), (7, "L3"), (8, "local16"), (6, "golden:slim_L4_nested_k6")])
+def test_fused_step_routing_up_to_eight_ranks(world, case):
+    """the fused step's routing (rotated destination lists, staging / send tile layout, head-row delivery) for the world sizes the
+    benchmark runs at: rank threads in this process over the numpy test double (remote stores are delivered at barriers, remote reads
+    come from snapshots), both backward transports, every rank against the protocol oracle"""
+    import threading
+    sys.path.insert(0, ROOT)
+    from arrow_matrix_b200 import synth
+    from arrow_matrix_b200.comm import ThreadWorld
+    from arrow_matrix_b200.sharded import ShardPlan, ShardedArrowEngine
+    from oracle import oracle
+    from tests.numpy_backend import GlooNumpyBackend
+    if case.startswith("golden:"):
+        from tests.golden_util import GoldenCase
+        g = GoldenCase(case.split(":", 1)[1])
+        dec, w, k, bd = g.decomposition, g.width, g.k, g.block_diagonal
+    else:
+        w, t0, k, levels, kind = {"L2": (8, 19, 4, 2, "random"), "L3": (8, 21, 3, 3, "random"), "banded": (8, 17, 4, 2, "random"),
+                                  "local16": (8, 16, 4, 2, "local")}[case]
+        bd = case != "banded"
+        dec = synth.synth_decomposition(t0, w, levels=levels, perm_kind=kind, seed=77, hub_rows=2, hub_nnz=40,
+                                        band_nnz=0 if bd else 3, shrink=2 if bd else 1)
+    po = oracle.ReferenceProtocolOracle(dec, w, k, block_diagonal=bd)
+    rng = np.random.default_rng(5)
+    Xs = [synth.generate_dense_matrix(po.rows[0], k, np.float32, rng) for _ in range(2)]
+    refs = []
+    for X in Xs:
+        po.set_features(X.copy())
+        refs.append(po.step().copy())
+        refs.append(po.step().copy())                       # a chained step after every fresh one
+    tw = ThreadWorld(world)
+    errors = [None] * world
+
+    def body(rank):
+        comm = tw.comm(rank)
+        try:
+            plan = ShardPlan(dec, w, rank, world, block_diagonal=bd)
+            eng = ShardedArrowEngine(plan, k, GlooNumpyBackend(comm, w, plan), overlap=bool(world % 3), mode="fused")
+            eng.bwd_mode = "pull" if world % 2 else "push"
+            sh0 = plan.levels[0]
+            i = 0
+            for X in Xs:
+                eng.set_features(X[sh0.r0:sh0.r1])
+                for _ in range(2):
+                    eng.step()
+                    got = eng.result(0)
+                    assert np.allclose(got, refs[i][sh0.r0:sh0.r1], rtol=1e-5, atol=1e-5 * max(1.0, float(np.max(np.abs(refs[i]))))), (rank, i)
+                    i += 1
+        except BaseException:     # noqa: BLE001
+            import traceback
+            errors[rank] = traceback.format_exc()
+            comm.abort()
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    real = [e for e in errors if e and "BrokenBarrierError" not in e]
+    assert not real and not any(errors), "\n".join(real or [e for e in errors if e])
